@@ -1,0 +1,165 @@
+/* paig_b200.h -- C ABI of libpaig_b200.so: the PhysicsNet per-sequence training step on B200 (sm_100a).
+ *
+ * The reference (Luka140/paig_reproduction) has no FFI / operator layer: its boundary for this path is
+ * the Python surface of PhysicsNet (nn/network/physics_models.py:40-245).  Every entry point below
+ * therefore cites the reference METHOD whose arithmetic it replaces; the Python mirror of that surface
+ * (paig_reproduction_b200/physics_models.py) binds them with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types.  All tensor pointers are DEVICE
+ *     pointers unless a name ends in _host.  The caller owns every buffer, including the workspace.
+ *   - Every function returns 0 on success, non-zero on error (paig_last_error() gives the text);
+ *     nothing throws across the ABI.  Work is enqueued on `stream` (a cudaStream_t passed as void*)
+ *     and is asynchronous with respect to the host.
+ *   - Tensors are dense row-major fp32 in the reference's own layouts (NCHW frames, [x0,y0,x1,y1,..]
+ *     position vectors); the physics scalars k/equil/g/m are fp64 device scalars as in the reference
+ *     (cells.py:27-29,91-93).
+ */
+#ifndef PAIG_B200_H
+#define PAIG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAIG_ABI_VERSION 1
+
+enum { PAIG_CELL_SPRING = 0, PAIG_CELL_BOUNCING = 1, PAIG_CELL_GRAVITY = 2 };
+
+/* One row of the runner's task table (runners/torch_run_physics.py:49-75) plus the constructor flags
+ * that change arithmetic (physics_models.py:41-55). */
+typedef struct paig_task {
+    int32_t cell;         /* PAIG_CELL_* : cells.py spring / bouncing / gravity */
+    int32_t n_objs;       /* COORD_UNITS/4, physics_models.py:31-37,95-96 */
+    int32_t H;            /* square frame side (32, 36, 64) */
+    int32_t seq_len;      /* frames per sequence given to forward (train or test length) */
+    int32_t input_steps;
+    int32_t pred_steps;
+    int32_t alt_vel;      /* VelocityEncoder alt_vel branch, blocks.py:33-41 */
+    int32_t deep_unet;    /* 0: ShallowUNet (H<40), 1: UNet (blocks.py:79-82) */
+    float alpha;          /* --autoencoder_loss weight, physics_models.py:137-139 */
+    int32_t batch_global; /* B of the whole job: loss normalisers use it (data-parallel shards pass the same value) */
+} paig_task;
+
+/* weight/bias pair of one Linear or Conv2d; NULL where the layer is absent or (in a gradient table) dead. */
+typedef struct paig_wb {
+    float* w;
+    float* b;
+} paig_wb;
+
+/* Parameter table: pointers into the caller's tensors, named after the reference state_dict.  The same
+ * struct type is used for the gradient table (each entry receives dL/dparam; all entries are WRITTEN,
+ * not accumulated, by paig_step_backward / paig_step_fused). */
+typedef struct paig_params {
+    paig_wb content_l1, content_l2;         /* var_net_content.l1/.l2        blocks.py:311-322 */
+    paig_wb background_l1, background_l2;   /* var_net_background.l1/.l2 */
+    paig_wb template_l1, template_l2;       /* var_net_template.l1/.l2 */
+    paig_wb conv[18];                       /* encoder.shallow_unet.c1..c13 or encoder.unet.c1..c18 */
+    paig_wb enc_l1, enc_l2, enc_l3;         /* encoder.l1..l3               blocks.py:70-75 */
+    paig_wb vel[3];                         /* velocity_encoder.init_vel_mlp.{0,2,4}, or [0]=init_vel_linear */
+    float* dt;                              /* rollout_cell.dt (fp32 scalar; never receives a gradient) */
+    double* phys0;                          /* spring: k      gravity: g      bouncing: NULL */
+    double* phys1;                          /* spring: equil  gravity: m (no gradient: A is recomputed from g,m; dm unused) */
+} paig_params;
+
+/* Outputs of the forward pass the reference caches on the module (physics_models.py:204-245). Any
+ * pointer may be NULL to skip materialising that tensor (paig_step_fused never writes frames). */
+typedef struct paig_outputs {
+    float* output_seq;    /* [B, T-in, 3, H, H]      conv_feedforward return value */
+    float* recons_out;    /* [B, in+pr, 3, H, H]     self.recons_out */
+    float* enc_pos;       /* [B, in+pr, 2n]          self.enc_pos */
+    float* pos_vel_seq;   /* [B, T-in+1, 4n]         self.pos_vel_seq */
+    float* enc_masks;     /* [B*(in+pr), n+1, H, H]  self.enc_masks */
+    float* masked_objs;   /* [n, B*(in+pr), 3, H, H] self.masked_objs (object-major) */
+    float* templates;     /* [n*t*t | n*3*t*t | 3*H*H] raw template, contents, background (pre-sigmoid) */
+    float* losses;        /* [4]: train, pred, extrap, recons  (compute_loss, physics_models.py:119-142) */
+} paig_outputs;
+
+int paig_abi_version(void);
+const char* paig_last_error(void);
+
+/* Bytes of scratch the step functions need for `B` local sequences of task `t`. */
+size_t paig_workspace_bytes(const paig_task* t, int B);
+
+/* ---- whole step ------------------------------------------------------------------------------- */
+
+/* conv_feedforward (physics_models.py:204-245) + compute_loss (:119-142), materialising every tensor
+ * requested in `out`.  x: [B, seq_len, 3, H, H].  Keeps what backward needs in `workspace`. */
+int paig_step_forward(const paig_task* t, const paig_params* p, const float* x, int B,
+                      const paig_outputs* out, void* workspace, void* stream);
+
+/* autograd backward of the step (base.py:151) given upstream gradients of the forward outputs.
+ * d_output_seq / d_recons_out / d_enc_pos / d_pos_vel_seq may be NULL (treated as zero: STALE mode,
+ * SURVEY Q1, passes d_output_seq = NULL).  Must follow paig_step_forward on the same workspace. */
+int paig_step_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x, int B,
+                       const float* d_output_seq, const float* d_recons_out, const float* d_enc_pos,
+                       const float* d_pos_vel_seq, void* workspace, void* stream);
+
+/* LIVE training step in one call: forward, the three losses and all parameter gradients of
+ * train = pred + alpha*recons, with the decoder's loss gradient formed in-kernel (no frames written).
+ * out->losses receives the four scalars; out->enc_pos / pos_vel_seq are written when non-NULL. */
+int paig_step_fused(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x, int B,
+                    const paig_outputs* out, void* workspace, void* stream);
+
+/* Same as paig_step_fused but with HOST buffers: x_host (pinned or pageable) is copied to the device
+ * staging area inside the workspace, and the four losses are copied back to losses_host.  This is the
+ * end-to-end call bench.py times as `e2e`. */
+int paig_step_fused_host(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x_host,
+                         int B, float* losses_host, void* workspace, void* stream);
+
+/* ---- stages (also used by the parity tests) ---------------------------------------------------- */
+
+/* cells.py:31-51 / 60-83 / 96-106 iterated `steps` times.  pos_vel_seq: [B, steps+1, 4n]; row 0 must
+ * already hold the initial state (pos || vel).  dt: fp32 scalar; phys0/phys1 as in paig_params. */
+int paig_rollout_forward(int cell, int n_objs, int B, int steps, const float* dt, const double* phys0,
+                         const double* phys1, float* pos_vel_seq, void* stream);
+
+/* Reverse sweep.  d_seq: [B, steps+1, 4n] upstream gradient of every row of pos_vel_seq (pos and vel parts).
+ * d_state0: [B, 4n] receives dL/d(initial pos||vel).  d_phys: [2] fp64, WRITTEN (dk, dequil | dg, 0). */
+int paig_rollout_backward(int cell, int n_objs, int B, int steps, const float* dt, const double* phys0,
+                          const double* phys1, const float* pos_vel_seq, const float* d_seq, float* d_state0,
+                          double* d_phys, void* stream);
+
+/* VariableFromNetwork x3 (blocks.py:318-322) + the decoder's constant preprocessing
+ * (physics_models.py:163-171,182): raw [n*t*t | 3n*t*t | 3*H*H], consts = [template+5 | sigmoid(contents) |
+ * sigmoid(background)], hidden [3*200] tanh activations kept for backward. */
+int paig_templates_forward(const paig_task* t, const paig_params* p, float* raw, float* consts, float* hidden,
+                           void* stream);
+int paig_templates_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* consts,
+                            const float* hidden, const float* d_consts, void* workspace, void* stream);
+
+/* conv_st_decoder + stn (physics_models.py:151-199, stn.py:5-16) for F frames.  loc: [F, 2n].
+ * frames (nullable): [F,3,H,H].  If target != NULL, sse[F] receives sum_chw (target-frame)^2 per frame;
+ * target frame f lives at target + (f / frames_per_seq) * target_seq_stride + (f % frames_per_seq) * 3*H*H. */
+int paig_decode_forward(const paig_task* t, const float* consts, const float* loc, int F, float* frames,
+                        const float* target, long target_seq_stride, int frames_per_seq, float* sse, void* stream);
+
+/* Decoder backward.  Either d_frames [F,3,H,H] is given, or (d_frames == NULL) the gradient is formed
+ * in-kernel as 2*scale[f % frames_per_seq]*(frame - target) (scale: device [frames_per_seq]).  d_loc [F,2n] is
+ * WRITTEN; d_consts (same layout as consts) is ACCUMULATED (caller zeroes it). sse nullable as above. */
+int paig_decode_backward(const paig_task* t, const float* consts, const float* loc, int F, const float* d_frames,
+                         const float* target, long target_seq_stride, int frames_per_seq, const float* scale,
+                         float* d_loc, float* d_consts, float* sse, void* stream);
+
+/* ConvolutionalEncoder.forward (blocks.py:77-103) on N frames; frame f is read at
+ * x + (f / frames_per_seq) * seq_stride + (f % frames_per_seq) * 3*H*H.  enc_pos: [N, 2n]. */
+int paig_encoder_forward(const paig_task* t, const paig_params* p, const float* x, long seq_stride,
+                         int frames_per_seq, int N, float* enc_pos, float* enc_masks, float* masked_objs,
+                         void* workspace, void* stream);
+int paig_encoder_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x,
+                          long seq_stride, int frames_per_seq, int N, const float* d_enc_pos, void* workspace,
+                          void* stream);
+
+/* VelocityEncoder.forward (blocks.py:31-49).  enc_pos: [B, enc_steps, 2n] -> vel [B, 2n]. */
+int paig_velocity_forward(const paig_task* t, const paig_params* p, const float* enc_pos, int B, float* vel,
+                          void* workspace, void* stream);
+int paig_velocity_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* enc_pos,
+                           int B, const float* d_vel, float* d_enc_pos_accum, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAIG_B200_H */
