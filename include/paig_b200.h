@@ -142,7 +142,7 @@ int paig_decode_forward(const paig_task* t, const float* consts, const float* lo
  * WRITTEN; d_consts (same layout as consts) is ACCUMULATED (caller zeroes it). sse nullable as above. */
 int paig_decode_backward(const paig_task* t, const float* consts, const float* loc, int F, const float* d_frames,
                          const float* target, long target_seq_stride, int frames_per_seq, const float* scale,
-                         float* d_loc, float* d_consts, float* sse, void* stream);
+                         float* d_loc, float* d_consts, float* sse, void* workspace, void* stream);
 
 /* ConvolutionalEncoder.forward (blocks.py:77-103) on N frames; frame f is read at
  * x + (f / frames_per_seq) * seq_stride + (f % frames_per_seq) * 3*H*H.  enc_pos: [N, 2n]. */

@@ -59,4 +59,62 @@ int paig_rollout_backward(int cell, int n_objs, int B, int steps, const float* d
                             (steps + 1) * rs, rs, 1, d_state0, d_phys, (cudaStream_t)stream);
 }
 
+int paig_templates_forward(const paig_task* t, const paig_params* p, float* raw, float* consts, float* hidden,
+                           void* stream) {
+    if (!valid_task(t)) return 1;
+    return templates_forward(t, p, raw, consts, hidden, (cudaStream_t)stream);
+}
+
+int paig_templates_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* consts,
+                            const float* hidden, const float* d_consts, void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    return templates_backward(t, p, grads, consts, hidden, d_consts, (float*)workspace, (cudaStream_t)stream);
+}
+
+static DecSeg flat_segment(const paig_task* t, const float* loc, int F, const float* target, long target_seq_stride,
+                           int frames_per_seq) {
+    DecSeg s;
+    s.nframes = F;
+    s.fps = frames_per_seq > 0 ? frames_per_seq : 1;
+    s.loc = loc;
+    s.loc_row_stride = 2L * t->n_objs;
+    s.loc_seq_stride = s.loc_row_stride * s.fps;
+    s.target = target;
+    s.tgt_seq_stride = target_seq_stride;
+    return s;
+}
+
+int paig_decode_forward(const paig_task* t, const float* consts, const float* loc, int F, float* frames,
+                        const float* target, long target_seq_stride, int frames_per_seq, float* sse, void* stream) {
+    if (!valid_task(t)) return 1;
+    DecSeg a = flat_segment(t, loc, F, target, target_seq_stride, frames_per_seq), b;
+    a.frames = frames;
+    a.sse = target ? sse : nullptr;
+    return decode_run(t, consts, a, b, false, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+int paig_decode_backward(const paig_task* t, const float* consts, const float* loc, int F, const float* d_frames,
+                         const float* target, long target_seq_stride, int frames_per_seq, const float* scale,
+                         float* d_loc, float* d_consts, float* sse, void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    if (!d_frames && !(target && scale)) {
+        set_error("decode_backward needs d_frames or (target and scale)");
+        return 1;
+    }
+    DecSeg a = flat_segment(t, loc, F, target, target_seq_stride, frames_per_seq), b;
+    a.dframes = d_frames;
+    a.scale = d_frames ? nullptr : scale;
+    a.sse = target ? sse : nullptr;
+    a.dloc = d_loc;
+    a.dloc_row_stride = a.loc_row_stride;
+    a.dloc_seq_stride = a.loc_seq_stride;
+    return decode_run(t, consts, a, b, true, (float*)workspace, d_consts, 1, (cudaStream_t)stream);
+}
+
+size_t paig_workspace_bytes(const paig_task* t, int B) {
+    if (!valid_task(t)) return 0;
+    (void)B;
+    return (decode_partials_floats(t) + templates_scratch_floats(t)) * sizeof(float);
+}
+
 }  // extern "C"

@@ -89,6 +89,44 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
     return scratch[32];
 }
 
+// Stage `bytes` (multiple of 16, both pointers 16-byte aligned) of global memory into shared memory with one
+// TMA bulk copy (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier; every thread of the block calls this
+// and returns once the data is visible.  `bar` is a block-shared 8-byte slot, `phase` the parity of this use.
+__device__ __forceinline__ void stage_bulk(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar,
+                                           unsigned phase) {
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+#if defined(PAIG_EMU)
+    (void)bar;
+    (void)phase;
+    const int nt = blockDim.x * blockDim.y * blockDim.z;
+    for (unsigned i = tid; i < bytes / 4; i += nt) ((float*)smem_dst)[i] = ((const float*)gmem_src)[i];
+    __syncthreads();
+#else
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(bar);
+    const unsigned dst_a = (unsigned)__cvta_generic_to_shared(smem_dst);
+    if (tid == 0) {
+        if (phase == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_a),
+            "l"(__cvta_generic_to_global(gmem_src)), "r"(bytes), "r"(bar_a)
+            : "memory");
+    }
+    __syncthreads();   // barrier initialised (phase 0) before anyone polls it
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(done)
+            : "r"(bar_a), "r"(phase & 1u)
+            : "memory");
+    }
+#endif
+}
+
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 inline int cdiv(long a, long b) { return (int)((a + b - 1) / b); }

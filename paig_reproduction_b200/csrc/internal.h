@@ -11,4 +11,30 @@ int rollout_backward(int cell, int n, int B, int steps, const float* dt, const d
                      const float* seq, const float* dpos, const float* dvel, long batch_stride, long row_stride,
                      int with_row0, float* d_state0, double* d_phys, cudaStream_t st);
 
+// decoder.cu -- a run of frames sharing one indexing rule (recons frames of all sequences, or rollout frames)
+struct DecSeg {
+    int nframes = 0;              // frames in this segment; frame fl has q = fl / fps, r = fl % fps
+    int fps = 1;
+    const float* loc = nullptr;   // object locations of frame (q,r) at loc + q*loc_seq_stride + r*loc_row_stride
+    long loc_seq_stride = 0, loc_row_stride = 0;
+    const float* target = nullptr;   // frame the output is compared with: target + q*tgt_seq_stride + r*3*H*H
+    long tgt_seq_stride = 0;
+    const float* scale = nullptr;    // [fps] loss weight s_r: in-kernel upstream gradient is 2*s_r*(out - target)
+    const float* dframes = nullptr;  // [nframes,3,H,H] upstream gradient from memory (overrides scale)
+    float* frames = nullptr;         // [nframes,3,H,H] decoded output (nullable)
+    float* sse = nullptr;            // [nframes] sum of squared error vs target (nullable)
+    float* dloc = nullptr;           // gradient wrt loc, indexed like loc with its own strides (nullable)
+    long dloc_seq_stride = 0, dloc_row_stride = 0;
+};
+int decode_run(const paig_task* t, const float* consts, const DecSeg& a, const DecSeg& b, bool bwd, float* partials,
+               float* d_consts, int accumulate, cudaStream_t st);
+size_t decode_partials_floats(const paig_task* t);
+
+// varnet.cu
+int templates_forward(const paig_task* t, const paig_params* p, float* raw, float* consts, float* hidden,
+                      cudaStream_t st);
+int templates_backward(const paig_task* t, const paig_params* p, const paig_params* g, const float* consts,
+                       const float* hidden, const float* d_consts, float* scratch, cudaStream_t st);
+size_t templates_scratch_floats(const paig_task* t);
+
 }  // namespace paig

@@ -108,6 +108,8 @@ template <typename T>
 static inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }   // fibers: one host thread
 static inline float atomicExch(float* p, float v) { float o = *p; *p = v; return o; }
 
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
 #define __expf(x) expf(x)
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }

@@ -10,6 +10,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from paig_reproduction_b200 import _abi  # noqa: E402
 
 _lib = None
 
@@ -19,18 +23,16 @@ def lib():
     if _lib is None:
         import build_emu
         _lib = ctypes.CDLL(build_emu.build())
-        _lib.paig_last_error.restype = ctypes.c_char_p
-        if hasattr(_lib, "paig_workspace_bytes"):
-            _lib.paig_workspace_bytes.restype = ctypes.c_size_t
+        _abi.declare(_lib)
     return _lib
 
 
 def ptr(a):
     """Device-pointer stand-in for a numpy array (None -> NULL)."""
     if a is None:
-        return ctypes.c_void_p(0)
+        return None
     assert a.flags["C_CONTIGUOUS"], "emu buffers must be contiguous"
-    return ctypes.c_void_p(a.ctypes.data)
+    return a.ctypes.data
 
 
 def check(rc):
@@ -44,3 +46,27 @@ def f32(x):
 
 def f64(x):
     return np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+
+
+def make_task(spec, seq_len=None, alpha=3.0, alt_vel=False, batch_global=0):
+    return _abi.Task(_abi.CELL_IDS[spec.cell], spec.n_objs, spec.H, seq_len or spec.seq_len, spec.input_steps,
+                     spec.pred_steps, int(alt_vel), int(spec.H >= 40), alpha, batch_global)
+
+
+def make_params(spec, arrays, alt_vel=False):
+    """arrays: dict state_dict-name -> numpy array (kept alive by the caller)."""
+    unet = "unet" if spec.H >= 40 else "shallow_unet"
+    n_convs = 18 if spec.H >= 40 else 13
+    p = _abi.Params()
+    _abi.fill_params(p, lambda k: arrays[k].ctypes.data, arrays.keys(), unet, n_convs, alt_vel, spec.cell)
+    return p
+
+
+def sd_to_numpy(sd):
+    return {k: np.ascontiguousarray(v.detach().numpy()) for k, v in sd.items()}
+
+
+def workspace(task, B):
+    n = lib().paig_workspace_bytes(ctypes.byref(task), B)
+    assert n > 0
+    return np.zeros(n // 4 + 64, np.float32)
