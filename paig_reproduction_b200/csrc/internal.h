@@ -37,4 +37,24 @@ int templates_backward(const paig_task* t, const paig_params* p, const paig_para
                        const float* hidden, const float* d_consts, float* scratch, cudaStream_t st);
 size_t templates_scratch_floats(const paig_task* t);
 
+// gemm.cu
+enum { EPI_NONE = 0, EPI_RELU = 1, EPI_TANH = 2, EPI_MASK_RELU = 3, EPI_MASK_TANH = 4 };
+struct GemmArgs {
+    const float* A = nullptr; long sam = 0, sak = 0;     // A(m,k) = A[m*sam + k*sak]
+    const float* B = nullptr; long sbk = 0, sbn = 0;     // B(k,n) = B[k*sbk + n*sbn]
+    float* C = nullptr; long ldc = 0;                    // C[m*ldc + n]
+    int M = 0, N = 0, K = 0;
+    const float* bias = nullptr;                         // [N] added before the epilogue
+    int epi = EPI_NONE;
+    const float* aux = nullptr; long ldaux = 0;          // activation the MASK_* epilogues differentiate
+    int accumulate = 0;                                  // C += result
+};
+int gemm(const GemmArgs& g, cudaStream_t st);
+int colsum(const float* X, int M, int N, int ld, float* out, cudaStream_t st);
+int linear_forward(const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int epi,
+                   cudaStream_t st);
+int linear_dgrad(const float* dY, const float* W, float* dX, int M, int K, int N, int epi, const float* aux,
+                 cudaStream_t st);
+int linear_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int K, int N, cudaStream_t st);
+
 }  // namespace paig
