@@ -159,6 +159,23 @@ int paig_velocity_forward(const paig_task* t, const paig_params* p, const float*
 int paig_velocity_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* enc_pos,
                            int B, const float* d_vel, float* d_enc_pos_accum, void* workspace, void* stream);
 
+/* ---- layer primitives (exported for unit tests of the encoder's building blocks) ------------------- */
+
+/* nn.Conv2d(Cin, Cout, 3, padding="same") (+ReLU) on x [N,Cin,S,S] -> y [N,Cout,S,S]   (blocks.py:246-276) */
+int paig_conv3x3_forward(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout, int S,
+                         int relu, void* stream);
+/* its backward: dy is the gradient of the (post-ReLU) output y; dx (nullable) [N,Cin,S,S], dw, db are WRITTEN.
+ * workspace: at least 296 * (Cout*Cin*9 + Cout) floats. */
+int paig_conv3x3_backward(const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
+                          float* db, int N, int Cin, int Cout, int S, int relu, void* workspace, void* stream);
+
+/* Test hook: offset (in floats) of a named workspace region ("act", "grad" with a UNet buffer index; "logits",
+ * "d_logits", "enc_pos", "d_enc_pos", "seq", "d_seq", "d_consts", "consts", "A", "dA"), or -1. */
+long paig_debug_workspace_offset(const paig_task* t, int B, const char* region, int index);
+/* Test hook: where the (post-ReLU) output of UNet conv `layer` (0-based) lives in the workspace:
+ * view[0] = offset in floats, view[1] = batch stride, view[2] = channels, view[3] = side, view[4] = has ReLU. */
+int paig_debug_unet_conv_view(const paig_task* t, int B, int layer, long view[5]);
+
 #ifdef __cplusplus
 }
 #endif

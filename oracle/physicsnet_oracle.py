@@ -197,9 +197,19 @@ def synthetic_frames(spec: TaskSpec, batch: int, seq_len: int, seed: int) -> Ten
 # ---------------------------------------------------------------------------
 # Encoder
 # ---------------------------------------------------------------------------
-def _conv(sd, key, x, relu):
+def _relu(y, force, name):
+    """ReLU; with ``force[name]`` (a 0/1 tensor of y's shape) the kink decisions are taken from it instead of from
+    sign(y).  Default (force=None) is the reference arithmetic.  Tests use forcing to compare gradients under
+    IDENTICAL ReLU decisions: an independent fp32 implementation flips a decision wherever |pre-activation| is
+    below rounding noise, which moves single-pixel gradient contributions between implementations."""
+    if force is not None and name in force:
+        return y * force[name]
+    return F.relu(y)
+
+
+def _conv(sd, key, x, relu, force=None):
     y = F.conv2d(x, sd[key + ".weight"], sd[key + ".bias"], padding="same")
-    return F.relu(y) if relu else y
+    return _relu(y, force, key.rsplit(".", 1)[1]) if relu else y
 
 
 def _up2(x):
@@ -210,9 +220,9 @@ def _up2(x):
     return F.interpolate(x, scale_factor=2, mode="bilinear", align_corners=False, antialias=True)
 
 
-def shallow_unet(sd: Dict[str, Tensor], x: Tensor, prefix: str = "encoder.shallow_unet.") -> Tensor:
+def shallow_unet(sd: Dict[str, Tensor], x: Tensor, prefix: str = "encoder.shallow_unet.", force=None) -> Tensor:
     """blocks.py:278-308.  ReLU after every conv except c7 and c10; c13 (1x1) keeps its ReLU (Q9)."""
-    c = lambda i, v, r=True: _conv(sd, prefix + "c%d" % i, v, r)
+    c = lambda i, v, r=True: _conv(sd, prefix + "c%d" % i, v, r, force)
     x1 = c(2, c(1, x))
     x2 = c(4, c(3, F.max_pool2d(x1, 2)))
     v = c(6, c(5, F.max_pool2d(x2, 2)))
@@ -223,9 +233,9 @@ def shallow_unet(sd: Dict[str, Tensor], x: Tensor, prefix: str = "encoder.shallo
     return c(13, v)
 
 
-def deep_unet(sd: Dict[str, Tensor], x: Tensor, prefix: str = "encoder.unet.") -> Tensor:
+def deep_unet(sd: Dict[str, Tensor], x: Tensor, prefix: str = "encoder.unet.", force=None) -> Tensor:
     """blocks.py:172-237.  No ReLU after c9, c12, c15, c18."""
-    c = lambda i, v, r=True: _conv(sd, prefix + "c%d" % i, v, r)
+    c = lambda i, v, r=True: _conv(sd, prefix + "c%d" % i, v, r, force)
     x1 = c(2, c(1, x))
     x2 = c(4, c(3, F.max_pool2d(x1, 2)))
     x3 = c(6, c(5, F.max_pool2d(x2, 2)))
@@ -239,10 +249,10 @@ def deep_unet(sd: Dict[str, Tensor], x: Tensor, prefix: str = "encoder.unet.") -
     return c(18, v, False)
 
 
-def encoder(sd: Dict[str, Tensor], frames: Tensor, spec: TaskSpec):
+def encoder(sd: Dict[str, Tensor], frames: Tensor, spec: TaskSpec, force=None):
     """blocks.py:77-103.  frames [N,3,H,H] -> (enc_pos [N,2n], enc_masks [N,n+1,H,H], masked_objs list)."""
     n, H = spec.n_objs, spec.H
-    logits = shallow_unet(sd, frames) if H < 40 else deep_unet(sd, frames)
+    logits = shallow_unet(sd, frames, force=force) if H < 40 else deep_unet(sd, frames, force=force)
     logits = torch.cat([logits, torch.ones_like(logits[:, :1])], 1)
     masks = torch.softmax(logits, 1)
     masked = [masks[:, o:o + 1] * frames for o in range(n)]
@@ -250,8 +260,8 @@ def encoder(sd: Dict[str, Tensor], frames: Tensor, spec: TaskSpec):
     if H >= 40:
         a = F.avg_pool2d(a, 2)
     a = a.reshape(a.shape[0], -1)
-    a = F.relu(F.linear(a, sd["encoder.l1.weight"], sd["encoder.l1.bias"]))
-    a = F.relu(F.linear(a, sd["encoder.l2.weight"], sd["encoder.l2.bias"]))
+    a = _relu(F.linear(a, sd["encoder.l1.weight"], sd["encoder.l1.bias"]), force, "l1")
+    a = _relu(F.linear(a, sd["encoder.l2.weight"], sd["encoder.l2.bias"]), force, "l2")
     a = F.linear(a, sd["encoder.l3.weight"], sd["encoder.l3.bias"])
     a = torch.cat(torch.split(a, a.shape[0] // n, 0), 1)       # [N, 2n] = x0,y0,x1,y1,...
     return torch.tanh(a) * (H / 2) + (H / 2), masks, masked
@@ -384,13 +394,13 @@ def decoder(sd: Dict[str, Tensor], loc: Tensor, spec: TaskSpec, learned=None, ex
 # ---------------------------------------------------------------------------
 # Whole step
 # ---------------------------------------------------------------------------
-def feedforward(sd: Dict[str, Tensor], x: Tensor, spec: TaskSpec, alt_vel: bool = False) -> Dict[str, Tensor]:
+def feedforward(sd: Dict[str, Tensor], x: Tensor, spec: TaskSpec, alt_vel: bool = False, force=None) -> Dict[str, Tensor]:
     """physics_models.py:204-245.  x [B,T,3,H,H]."""
     B, T = x.shape[0], x.shape[1]
     n, H, e = spec.n_objs, spec.H, spec.enc_steps
     assert T > e
     frames = x[:, :e].reshape(B * e, 3, H, H)
-    enc_pos, masks, masked = encoder(sd, frames, spec)
+    enc_pos, masks, masked = encoder(sd, frames, spec, force)
     learned = learned_tensors(sd, spec)
     recons = decoder(sd, enc_pos, spec, learned).reshape(B, e, 3, H, H)
     enc_pos = enc_pos.reshape(B, e, 2 * n)
@@ -420,13 +430,13 @@ def losses(x: Tensor, ff: Dict[str, Tensor], spec: TaskSpec, alpha: float) -> Di
     return dict(train=train, pred=pred, extrap=extrap, recons=recons, per_frame_pred=per)
 
 
-def live_step(sd: Dict[str, Tensor], x: Tensor, spec: TaskSpec, alpha: float, alt_vel: bool = False):
+def live_step(sd: Dict[str, Tensor], x: Tensor, spec: TaskSpec, alpha: float, alt_vel: bool = False, force=None):
     """One LIVE-mode training step: forward, loss, backward.  Returns
     (feedforward dict, losses dict, grads dict) -- grads only for tensors that receive one."""
     leaves = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k != "rollout_cell.dt"
                                                    and k != "rollout_cell.m")
               for k, v in sd.items()}
-    ff = feedforward(leaves, x, spec, alt_vel)
+    ff = feedforward(leaves, x, spec, alt_vel, force)
     ls = losses(x, ff, spec, alpha)
     ls["train"].backward()
     grads = {k: v.grad for k, v in leaves.items() if v.grad is not None}

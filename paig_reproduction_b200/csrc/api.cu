@@ -21,7 +21,7 @@ int check_launch(const char* what) {
     return 0;
 }
 
-static bool valid_task(const paig_task* t) {
+bool valid_task(const paig_task* t) {
     if (!t) {
         set_error("task is NULL");
         return false;
@@ -111,10 +111,32 @@ int paig_decode_backward(const paig_task* t, const float* consts, const float* l
     return decode_run(t, consts, a, b, true, (float*)workspace, d_consts, 1, (cudaStream_t)stream);
 }
 
-size_t paig_workspace_bytes(const paig_task* t, int B) {
-    if (!valid_task(t)) return 0;
-    (void)B;
-    return (decode_partials_floats(t) + templates_scratch_floats(t)) * sizeof(float);
+int paig_conv3x3_forward(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout, int S,
+                         int relu, void* stream) {
+    ConvArgs a;
+    a.in = x; a.in_bs = (long)Cin * S * S; a.Cin = Cin;
+    a.w = w; a.b = b;
+    a.out = y; a.out_bs = (long)Cout * S * S; a.Cout = Cout;
+    a.S = S; a.N = N; a.relu = relu;
+    return conv3x3(a, (cudaStream_t)stream);
+}
+
+int paig_conv3x3_backward(const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
+                          float* db, int N, int Cin, int Cout, int S, int relu, void* workspace, void* stream) {
+    WgradArgs g;
+    g.in = x; g.in_bs = (long)Cin * S * S; g.Cin = Cin;
+    g.g = dy; g.g_bs = (long)Cout * S * S; g.Cout = Cout;
+    g.act = relu ? y : nullptr; g.act_bs = g.g_bs;
+    g.S = S; g.N = N; g.partials = (float*)workspace;
+    int rc = conv3x3_wgrad(g, dw, db, (cudaStream_t)stream);
+    if (rc || !dx) return rc;
+    ConvArgs a;
+    a.in = dy; a.in_bs = g.g_bs; a.Cin = Cout;
+    a.mask = relu ? y : nullptr; a.mask_bs = g.g_bs;
+    a.w = w; a.transposed = 1;
+    a.out = dx; a.out_bs = g.in_bs; a.Cout = Cin;
+    a.S = S; a.N = N;
+    return conv3x3(a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,568 @@
+// fp32 CUDA-core convolution kernels for the encoder UNets (blocks.py:106-308): 3x3 "same" convolution
+// forward, its data gradient (the same kernel run on the masked output gradient with transposed, flipped
+// weights) and its weight/bias gradient; the 1x1 head; 2x2 max-pool and the exact-2x bilinear upsample
+// (tvtrans.Resize, blocks.py:260,269) with their adjoints.
+//
+// Every tensor is a channel-sliced view of an NCHW buffer: element (n,c,y,x) = p[n*bs + (c*S + y)*S + x].
+// Concats of the UNet are realised by producers writing into channel slices of one buffer.
+//
+// Why CUDA cores and not tcgen05 here: output-channel counts are 8..32 and the step must match the
+// reference to 1e-4 (single-pass TF32 is ~1e-3); see DESIGN.md for the ncu evidence.
+#include "common.cuh"
+#include "internal.h"
+
+namespace paig {
+
+constexpr int kConvThreads = 256;
+constexpr int kCK = 8;                 // input channels staged per pass
+
+// ---------------------------------------------------------------------------------------------------------
+// conv3x3: each thread produces 4 horizontally adjacent pixels x CO_T output channels.
+// Block = FPB frames x TH rows x QX quads (<= 256 threads); blockIdx = (frame group, row strip, cout group).
+// ---------------------------------------------------------------------------------------------------------
+template <int CO_T>
+__global__ void __launch_bounds__(kConvThreads) conv3x3_kernel(ConvArgs a) {
+    PAIG_DYN_SMEM(float, smem);
+    const int S = a.S, QX = a.QX, TH = a.TH, FPB = a.FPB;
+    const int PITCH = 4 * QX + 4;
+    const int plane = (TH + 2) * PITCH;
+    float* sIn = smem;                                    // [FPB][kCK][TH+2][PITCH]
+    float* sW = smem + FPB * kCK * plane;                 // [kCK][9][CO_T]
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int qx = tid % QX, ty = (tid / QX) % TH, fb = tid / (QX * TH);
+    const int f0 = blockIdx.x * FPB, y0 = blockIdx.y * TH, co0 = blockIdx.z * CO_T;
+    const int y = y0 + ty, f = f0 + fb;
+    const bool active = fb < FPB && f < a.N && y < S;
+
+    float acc[CO_T][4];
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[c][p] = 0.f;
+
+    for (int c0 = 0; c0 < a.Cin; c0 += kCK) {
+        const int nc = min(kCK, a.Cin - c0);
+        // ---- stage the input tile (zero halo), optionally masked by the producer's ReLU ----
+        const int tile_elems = FPB * nc * plane;
+        for (int e = tid; e < tile_elems; e += nthr) {
+            const int col = e % PITCH, r = (e / PITCH) % (TH + 2), ci = (e / plane) % nc, ff = e / (plane * nc);
+            const int gy = y0 + r - 1, gx = col - 1, gf = f0 + ff;
+            float v = 0.f;
+            if (gf < a.N && (unsigned)gy < (unsigned)S && (unsigned)gx < (unsigned)S) {
+                const long off = ((long)(c0 + ci) * S + gy) * S + gx;
+                v = a.in[(long)gf * a.in_bs + off];
+                if (a.mask && !(a.mask[(long)gf * a.mask_bs + off] > 0.f)) v = 0.f;
+            }
+            sIn[(ff * kCK + ci) * plane + r * PITCH + col] = v;
+        }
+        // ---- stage the weights of this (cin chunk, cout group): sW[ci][tap][co] ----
+        for (int e = tid; e < nc * 9 * CO_T; e += nthr) {
+            const int co = e % CO_T, tap = (e / CO_T) % 9, ci = e / (9 * CO_T);
+            float v = 0.f;
+            if (co0 + co < a.Cout) {
+                v = a.transposed ? a.w[((long)(c0 + ci) * a.Cout + (co0 + co)) * 9 + (8 - tap)]
+                                 : a.w[((long)(co0 + co) * a.Cin + (c0 + ci)) * 9 + tap];
+            }
+            sW[(ci * 9 + tap) * CO_T + co] = v;
+        }
+        __syncthreads();
+        if (active) {
+            for (int ci = 0; ci < nc; ++ci) {
+                const float* row = sIn + (fb * kCK + ci) * plane + ty * PITCH + 4 * qx;
+                float v[3][6];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float4 p4 = *reinterpret_cast<const float4*>(row + r * PITCH);
+                    const float2 p2 = *reinterpret_cast<const float2*>(row + r * PITCH + 4);
+                    v[r][0] = p4.x; v[r][1] = p4.y; v[r][2] = p4.z; v[r][3] = p4.w; v[r][4] = p2.x; v[r][5] = p2.y;
+                }
+                const float* wp = sW + ci * 9 * CO_T;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float* w = wp + (ky * 3 + kx) * CO_T;
+#pragma unroll
+                        for (int c4 = 0; c4 < CO_T; c4 += 4) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(w + c4);
+                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                                for (int p = 0; p < 4; ++p) acc[c4 + c][p] += wv[c] * v[ky][kx + p];
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+    const int x0 = 4 * qx;
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) {
+        const int co = co0 + c;
+        if (co >= a.Cout) break;
+        const float bias = a.b ? a.b[co] : 0.f;
+        float o[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            o[p] = acc[c][p] + bias;
+            if (a.relu) o[p] = fmaxf(o[p], 0.f);
+        }
+        float* dst = a.out + (long)f * a.out_bs + ((long)co * S + y) * S + x0;
+        if (x0 + 3 < S && (S & 3) == 0 && (a.out_bs & 3) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                if (x0 + p < S) dst[p] = o[p];
+        }
+    }
+}
+
+static void conv_geometry(int S, int N, int* QX, int* TH, int* FPB, int* strips) {
+    *QX = (S + 3) / 4;
+    const int per_frame = *QX * S;
+    if (per_frame <= kConvThreads) {
+        *TH = S;
+        *strips = 1;
+        *FPB = kConvThreads / per_frame;
+        if (*FPB > N) *FPB = N;
+        if (*FPB > 16) *FPB = 16;
+    } else {
+        *strips = cdiv(per_frame, kConvThreads);
+        *TH = cdiv(S, *strips);
+        *FPB = 1;
+    }
+}
+
+int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
+    ConvArgs a = in_args;
+    if (a.N <= 0) return 0;
+    int strips;
+    conv_geometry(a.S, a.N, &a.QX, &a.TH, &a.FPB, &strips);
+    const int PITCH = 4 * a.QX + 4;
+    const int threads = ((a.FPB * a.TH * a.QX + 31) / 32) * 32;
+    const bool wide = (a.Cout % 16) == 0;
+    const int CO_T = wide ? 16 : 8;
+    const size_t smem = ((size_t)a.FPB * kCK * (a.TH + 2) * PITCH + (size_t)kCK * 9 * CO_T) * sizeof(float);
+    dim3 grid(cdiv(a.N, a.FPB), strips, cdiv(a.Cout, CO_T));
+    if (wide) launch(conv3x3_kernel<16>, grid, dim3(threads), smem, st, a);
+    else launch(conv3x3_kernel<8>, grid, dim3(threads), smem, st, a);
+    return check_launch("conv3x3");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// conv3x3 weight + bias gradient.  A thread owns the 3x3 taps of (4 output channels x 1 input channel) and a
+// partition of the pixels; accumulators live in registers across every (frame, row strip) item the CTA
+// walks; pixel partitions are folded through shared memory at the end and each CTA leaves one partial.
+//   dW[co,ci,ky,kx] = sum_{n,y,x} g[n,co,y,x] * in[n,ci,y+ky-1,x+kx-1],   g = dOut * (act > 0)
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kWgTH = 8;                  // rows per staged strip
+
+__global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a) {
+    PAIG_DYN_SMEM(float, smem);
+    const int S = a.S, QX = (S + 3) / 4;
+    const int PITCH = 4 * QX + 4;
+    const int in_plane = a.in_plane, g_plane = a.g_plane;            // padded to == 4 (mod 32) floats
+    float* sIn = smem;                                                // [Cin][kWgTH+2][PITCH]
+    float* sG = smem + (size_t)a.Cin * in_plane;                      // [Cout][kWgTH][PITCH-4 .. ] pitch 4*QX
+    const int GP = 4 * QX;
+    const int tid = threadIdx.x;
+    const int cob_n = (a.Cout + 3) / 4;
+    const int G = cob_n * a.Cin;                                      // owner groups
+    const int gsets = gridDim.y;
+    const int G_per = (G + gsets - 1) / gsets;                        // groups handled by this CTA (<= 256)
+    const int P = max(1, kConvThreads / G_per);                       // pixel partitions
+    const int grp_local = tid % G_per, part = tid / G_per;
+    const int grp = blockIdx.y * G_per + grp_local;
+    const bool owner = part < P && grp < G;
+    const int ci = owner ? grp % a.Cin : 0, cob = owner ? grp / a.Cin : 0;
+
+    float acc[4][9];
+    float bacc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        bacc[c] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
+    }
+    const int strips = (S + kWgTH - 1) / kWgTH;
+    const int items = a.N * strips;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int f = item / strips, y0 = (item % strips) * kWgTH;
+        const int rows = min(kWgTH, S - y0);
+        // ---- stage input strip (halo rows/cols zero) ----
+        for (int e = tid; e < a.Cin * (kWgTH + 2) * PITCH; e += kConvThreads) {
+            const int col = e % PITCH, r = (e / PITCH) % (kWgTH + 2), c = e / (PITCH * (kWgTH + 2));
+            const int gy = y0 + r - 1, gx = col - 1;
+            float v = 0.f;
+            if (r < rows + 2 && (unsigned)gy < (unsigned)S && (unsigned)gx < (unsigned)S) {
+                const long off = ((long)c * S + gy) * S + gx;
+                v = a.in[(long)f * a.in_bs + off];
+                if (a.in_mask && !(a.in_mask[(long)f * a.in_mask_bs + off] > 0.f)) v = 0.f;
+            }
+            sIn[c * in_plane + r * PITCH + col] = v;
+        }
+        // ---- stage masked output gradient strip ----
+        for (int e = tid; e < a.Cout * kWgTH * GP; e += kConvThreads) {
+            const int col = e % GP, r = (e / GP) % kWgTH, c = e / (GP * kWgTH);
+            float v = 0.f;
+            if (r < rows && col < S) {
+                const long off = ((long)c * S + (y0 + r)) * S + col;
+                v = a.g[(long)f * a.g_bs + off];
+                if (a.act && !(a.act[(long)f * a.act_bs + off] > 0.f)) v = 0.f;
+            }
+            sG[c * g_plane + r * GP + col] = v;
+        }
+        __syncthreads();
+        if (owner) {
+            const int nq = rows * QX;
+            for (int q = part; q < nq; q += P) {
+                const int r = q / QX, x0 = (q % QX) * 4;
+                float v[3][6];
+                const float* ip = sIn + ci * in_plane + r * PITCH + x0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float4 p4 = *reinterpret_cast<const float4*>(ip + k * PITCH);
+                    const float2 p2 = *reinterpret_cast<const float2*>(ip + k * PITCH + 4);
+                    v[k][0] = p4.x; v[k][1] = p4.y; v[k][2] = p4.z; v[k][3] = p4.w; v[k][4] = p2.x; v[k][5] = p2.y;
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int co = cob * 4 + c;
+                    if (co < a.Cout) {
+                        const float4 g4 = *reinterpret_cast<const float4*>(sG + co * g_plane + r * GP + x0);
+                        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                        bacc[c] += (gv[0] + gv[1]) + (gv[2] + gv[3]);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+                                for (int p = 0; p < 4; ++p) acc[c][ky * 3 + kx] += gv[p] * v[ky][kx + p];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- fold pixel partitions (fixed order) and write this CTA's partial ----
+    float* sRed = smem;                                       // [P][G_per][40]  (reuses the tile area)
+    if (owner) {
+        float* dst = sRed + ((size_t)part * G_per + grp_local) * 40;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int t = 0; t < 9; ++t) dst[c * 9 + t] = acc[c][t];
+            dst[36 + c] = bacc[c];
+        }
+    }
+    __syncthreads();
+    const int nW = a.Cout * a.Cin * 9;
+    float* out = a.partials + (size_t)blockIdx.x * (nW + a.Cout);
+    for (int e = tid; e < G_per * 40; e += kConvThreads) {
+        const int k = e % 40, gl = e / 40;
+        const int gg = blockIdx.y * G_per + gl;
+        if (gg >= G) continue;
+        float s = 0.f;
+        for (int p = 0; p < P; ++p) s += sRed[((size_t)p * G_per + gl) * 40 + k];
+        const int gci = gg % a.Cin, gcob = gg / a.Cin;
+        if (k < 36) {
+            const int co = gcob * 4 + k / 9;
+            if (co < a.Cout) out[((size_t)co * a.Cin + gci) * 9 + (k % 9)] = s;
+        } else if (gci == 0) {
+            const int co = gcob * 4 + (k - 36);
+            if (co < a.Cout) out[nW + co] = s;
+        }
+    }
+}
+
+// out[i] = sum_p partials[p*stride + i]   (fixed order => deterministic); two destinations (weights, bias).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int stride,
+                                                              int n0, float* __restrict__ out0, int n1,
+                                                              float* __restrict__ out1) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n0 + n1) return;
+    float s = 0.f;
+    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * stride + i];
+    if (i < n0) out0[i] = s;
+    else if (out1) out1[i - n0] = s;
+}
+
+int reduce_partials(const float* partials, int nparts, int stride, int n0, float* out0, int n1, float* out1,
+                    cudaStream_t st) {
+    launch(reduce_partials_kernel, dim3(cdiv(n0 + n1, 256)), dim3(256), 0, st, partials, nparts, stride, n0, out0, n1,
+           out1);
+    return check_launch("reduce_partials");
+}
+
+static int pad_plane(int n) {          // smallest m >= n with m % 32 == 4: conflict-free 16-byte loads across channels
+    int m = n + ((4 - n) % 32 + 32) % 32;
+    return m;
+}
+
+size_t wgrad_partials_floats(int Cin, int Cout) { return (size_t)kWgradMaxCtas * ((size_t)Cout * Cin * 9 + Cout); }
+
+int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t st) {
+    WgradArgs a = in_args;
+    if (a.N <= 0) return 0;
+    const int QX = (a.S + 3) / 4, PITCH = 4 * QX + 4;
+    a.in_plane = pad_plane((kWgTH + 2) * PITCH);
+    a.g_plane = pad_plane(kWgTH * 4 * QX);
+    const int G = ((a.Cout + 3) / 4) * a.Cin;
+    const int gsets = cdiv(G, kConvThreads);
+    const int G_per = cdiv(G, gsets);
+    const int P = kConvThreads / G_per > 0 ? kConvThreads / G_per : 1;
+    const size_t tile = (size_t)a.Cin * a.in_plane + (size_t)a.Cout * a.g_plane;
+    const size_t red = (size_t)P * G_per * 40;
+    const size_t smem = (tile > red ? tile : red) * sizeof(float);
+    if (smem > 220 * 1024) {
+        set_error("conv3x3_wgrad: %d->%d channels at %d px needs %zu B of shared memory", a.Cin, a.Cout, a.S, smem);
+        return 1;
+    }
+    const int strips = cdiv(a.S, kWgTH);
+    int ctas = a.N * strips;
+    if (ctas > kWgradMaxCtas) ctas = kWgradMaxCtas;
+    launch(conv3x3_wgrad_kernel, dim3(ctas, gsets), dim3(kConvThreads), smem, st, a);
+    int rc = check_launch("conv3x3_wgrad");
+    if (rc) return rc;
+    const int nW = a.Cout * a.Cin * 9;
+    return reduce_partials(a.partials, ctas, nW + a.Cout, nW, dW, a.Cout, db, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 1x1 head (blocks.py:236,307): Cin in {8,16} -> Cout = n_objs.  One thread per pixel.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kMaxHeadIn = 16;
+
+__global__ void __launch_bounds__(256) conv1x1_fwd_kernel(const float* __restrict__ in, long in_bs, int Cin,
+                                                          const float* __restrict__ w, const float* __restrict__ b,
+                                                          float* __restrict__ out, long out_bs, int Cout, int HW, int N,
+                                                          int relu) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * HW) return;
+    const int f = (int)(idx / HW), p = (int)(idx % HW);
+    float v[kMaxHeadIn];
+#pragma unroll
+    for (int c = 0; c < kMaxHeadIn; ++c) v[c] = c < Cin ? in[(long)f * in_bs + (long)c * HW + p] : 0.f;
+    for (int co = 0; co < Cout; ++co) {
+        float s = b[co];
+#pragma unroll
+        for (int c = 0; c < kMaxHeadIn; ++c)
+            if (c < Cin) s += w[co * Cin + c] * v[c];
+        if (relu) s = fmaxf(s, 0.f);
+        out[(long)f * out_bs + (long)co * HW + p] = s;
+    }
+}
+
+// dIn written; per-block partials of dW [Cout*Cin] and db [Cout].
+__global__ void __launch_bounds__(256) conv1x1_bwd_kernel(const float* __restrict__ in, long in_bs, int Cin,
+                                                          const float* __restrict__ w, const float* __restrict__ dout,
+                                                          long dout_bs, const float* __restrict__ act, long act_bs,
+                                                          int Cout, int HW, int N, float* __restrict__ din, long din_bs,
+                                                          float* __restrict__ partials) {
+    __shared__ float red[8][kMaxObjs * (kMaxHeadIn + 1)];
+    float aw[kMaxObjs][kMaxHeadIn], ab[kMaxObjs];
+#pragma unroll
+    for (int o = 0; o < kMaxObjs; ++o) {
+        ab[o] = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMaxHeadIn; ++c) aw[o][c] = 0.f;
+    }
+    const long total = (long)N * HW;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int f = (int)(idx / HW), p = (int)(idx % HW);
+        float g[kMaxObjs];
+#pragma unroll
+        for (int o = 0; o < kMaxObjs; ++o) {
+            g[o] = 0.f;
+            if (o < Cout) {
+                g[o] = dout[(long)f * dout_bs + (long)o * HW + p];
+                if (act && !(act[(long)f * act_bs + (long)o * HW + p] > 0.f)) g[o] = 0.f;
+                ab[o] += g[o];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < kMaxHeadIn; ++c) {
+            if (c < Cin) {
+                const float v = in[(long)f * in_bs + (long)c * HW + p];
+                float d = 0.f;
+#pragma unroll
+                for (int o = 0; o < kMaxObjs; ++o)
+                    if (o < Cout) {
+                        aw[o][c] += g[o] * v;
+                        d += w[o * Cin + c] * g[o];
+                    }
+                din[(long)f * din_bs + (long)c * HW + p] = d;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 0; o < kMaxObjs; ++o) {
+#pragma unroll
+        for (int c = 0; c < kMaxHeadIn; ++c) {
+            const float s = warp_sum(aw[o][c]);
+            if (lane == 0) red[wid][o * (kMaxHeadIn + 1) + c] = s;
+        }
+        const float sb = warp_sum(ab[o]);
+        if (lane == 0) red[wid][o * (kMaxHeadIn + 1) + kMaxHeadIn] = sb;
+    }
+    __syncthreads();
+    const int nW = Cout * Cin;
+    for (int e = threadIdx.x; e < nW + Cout; e += blockDim.x) {
+        const int o = e < nW ? e / Cin : e - nW, c = e < nW ? e % Cin : kMaxHeadIn;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][o * (kMaxHeadIn + 1) + c];
+        partials[(size_t)blockIdx.x * (nW + Cout) + e] = s;
+    }
+}
+
+int conv1x1_forward(const float* in, long in_bs, int Cin, const float* w, const float* b, float* out, long out_bs,
+                    int Cout, int S, int N, int relu, cudaStream_t st) {
+    if (Cin > kMaxHeadIn || Cout > kMaxObjs) {
+        set_error("conv1x1: %d->%d channels unsupported", Cin, Cout);
+        return 1;
+    }
+    launch(conv1x1_fwd_kernel, dim3(cdiv((long)N * S * S, 256)), dim3(256), 0, st, in, in_bs, Cin, w, b, out, out_bs,
+           Cout, S * S, N, relu);
+    return check_launch("conv1x1_fwd");
+}
+
+int conv1x1_backward(const float* in, long in_bs, int Cin, const float* w, const float* dout, long dout_bs,
+                     const float* act, long act_bs, int Cout, int S, int N, float* din, long din_bs, float* dW,
+                     float* db, float* partials, cudaStream_t st) {
+    if (Cin > kMaxHeadIn || Cout > kMaxObjs) {
+        set_error("conv1x1: %d->%d channels unsupported", Cin, Cout);
+        return 1;
+    }
+    int blocks = cdiv((long)N * S * S, 256 * 4);
+    if (blocks > 592) blocks = 592;
+    launch(conv1x1_bwd_kernel, dim3(blocks), dim3(256), 0, st, in, in_bs, Cin, w, dout, dout_bs, act, act_bs, Cout,
+           S * S, N, din, din_bs, partials);
+    int rc = check_launch("conv1x1_bwd");
+    if (rc) return rc;
+    return reduce_partials(partials, blocks, Cout * Cin + Cout, Cout * Cin, dW, Cout, db, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 2x2 max-pool (blocks.py:281,284) and its adjoint (first maximum in row-major window order wins, as ATen).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ in, long in_bs, float* __restrict__ out,
+                                                       long out_bs, int C, int So, long total) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % So), y = (int)((idx / So) % So), c = (int)((idx / ((long)So * So)) % C);
+    const long f = idx / ((long)So * So * C);
+    const int Si = 2 * So;
+    const float* p = in + f * in_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
+    const float m = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[Si], p[Si + 1]));
+    out[f * out_bs + ((long)c * So + y) * So + x] = m;
+}
+
+// din[window argmax] += dout   (din is the gradient of the pooled tensor's source; other entries untouched)
+__global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ in, long in_bs,
+                                                           const float* __restrict__ dout, long dout_bs,
+                                                           float* __restrict__ din, long din_bs, int C, int So,
+                                                           long total) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % So), y = (int)((idx / So) % So), c = (int)((idx / ((long)So * So)) % C);
+    const long f = idx / ((long)So * So * C);
+    const int Si = 2 * So;
+    const long o = ((long)c * Si + 2 * y) * Si + 2 * x;
+    const float* p = in + f * in_bs + o;
+    int best = 0;
+    float m = p[0];
+    if (p[1] > m) { m = p[1]; best = 1; }
+    if (p[Si] > m) { m = p[Si]; best = Si; }
+    if (p[Si + 1] > m) { m = p[Si + 1]; best = Si + 1; }
+    din[f * din_bs + o + best] += dout[f * dout_bs + ((long)c * So + y) * So + x];
+}
+
+int maxpool2(const float* in, long in_bs, float* out, long out_bs, int C, int So, int N, cudaStream_t st) {
+    const long total = (long)N * C * So * So;
+    if (total <= 0) return 0;
+    launch(maxpool2_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, in, in_bs, out, out_bs, C, So, total);
+    return check_launch("maxpool2");
+}
+int maxpool2_backward(const float* in, long in_bs, const float* dout, long dout_bs, float* din, long din_bs, int C,
+                      int So, int N, cudaStream_t st) {
+    const long total = (long)N * C * So * So;
+    if (total <= 0) return 0;
+    launch(maxpool2_bwd_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, in, in_bs, dout, dout_bs, din, din_bs, C, So,
+           total);
+    return check_launch("maxpool2_bwd");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// exact 2x bilinear upsample, align_corners=False (tvtrans.Resize on a tensor):
+//   out[2i] = .25 in[i-1] + .75 in[i],  out[2i+1] = .75 in[i] + .25 in[i+1],  indices clamped; separable.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up_taps(int o, int Si, int& i0, int& i1, float& w0, float& w1) {
+    const int k = o >> 1;
+    if (o & 1) { i0 = k; i1 = min(k + 1, Si - 1); w0 = 0.75f; w1 = 0.25f; }
+    else { i0 = max(k - 1, 0); i1 = k; w0 = 0.25f; w1 = 0.75f; }
+}
+
+__global__ void __launch_bounds__(256) upsample2_kernel(const float* __restrict__ in, long in_bs, float* __restrict__ out,
+                                                        long out_bs, int C, int Si, long total) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int So = 2 * Si;
+    const int x = (int)(idx % So), y = (int)((idx / So) % So), c = (int)((idx / ((long)So * So)) % C);
+    const long f = idx / ((long)So * So * C);
+    int xa, xb, ya, yb;
+    float wxa, wxb, wya, wyb;
+    up_taps(x, Si, xa, xb, wxa, wxb);
+    up_taps(y, Si, ya, yb, wya, wyb);
+    const float* p = in + f * in_bs + (long)c * Si * Si;
+    const float top = wxa * p[ya * Si + xa] + wxb * p[ya * Si + xb];      // W pass, then H pass (ATen's order)
+    const float bot = wxa * p[yb * Si + xa] + wxb * p[yb * Si + xb];
+    out[f * out_bs + ((long)c * So + y) * So + x] = wya * top + wyb * bot;
+}
+
+// adjoint: din[i,j] = sum over the (<= 4x4) outputs that read in[i,j] of weight * dout   (gather, written)
+__device__ __forceinline__ float up_weight(int o, int i, int Si) {
+    int i0, i1;
+    float w0, w1;
+    up_taps(o, Si, i0, i1, w0, w1);
+    return (i0 == i ? w0 : 0.f) + (i1 == i ? w1 : 0.f);
+}
+
+__global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restrict__ dout, long dout_bs,
+                                                            float* __restrict__ din, long din_bs, int C, int Si,
+                                                            long total) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int So = 2 * Si;
+    const int j = (int)(idx % Si), i = (int)((idx / Si) % Si), c = (int)((idx / ((long)Si * Si)) % C);
+    const long f = idx / ((long)Si * Si * C);
+    const float* g = dout + f * dout_bs + (long)c * So * So;
+    float s = 0.f;
+    for (int oy = max(2 * i - 1, 0); oy <= min(2 * i + 2, So - 1); ++oy) {
+        const float wy = up_weight(oy, i, Si);
+        if (wy == 0.f) continue;
+        float r = 0.f;
+        for (int ox = max(2 * j - 1, 0); ox <= min(2 * j + 2, So - 1); ++ox) r += up_weight(ox, j, Si) * g[oy * So + ox];
+        s += wy * r;
+    }
+    din[f * din_bs + ((long)c * Si + i) * Si + j] = s;
+}
+
+int upsample2(const float* in, long in_bs, float* out, long out_bs, int C, int Si, int N, cudaStream_t st) {
+    const long total = (long)N * C * 4 * Si * Si;
+    if (total <= 0) return 0;
+    launch(upsample2_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, in, in_bs, out, out_bs, C, Si, total);
+    return check_launch("upsample2");
+}
+int upsample2_backward(const float* dout, long dout_bs, float* din, long din_bs, int C, int Si, int N, cudaStream_t st) {
+    const long total = (long)N * C * Si * Si;
+    if (total <= 0) return 0;
+    launch(upsample2_bwd_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, dout, dout_bs, din, din_bs, C, Si, total);
+    return check_launch("upsample2_bwd");
+}
+
+}  // namespace paig

@@ -1,0 +1,604 @@
+// ConvolutionalEncoder (blocks.py:52-103) and VelocityEncoder (blocks.py:8-49): forward and hand-written backward.
+//
+// The two UNets (ShallowUNet blocks.py:240-308 for H < 40, UNet blocks.py:106-237 otherwise) are described
+// as data (layout.h: buffers + op list) and executed by one small interpreter, forward and in reverse.  The
+// skip concats are channel slices of shared buffers, so "cat" costs nothing.  Every activation is kept in the
+// workspace for the backward pass (440 KB per 32x32 frame; the step is compute-bound, not HBM-bound).
+#include "common.cuh"
+#include "internal.h"
+#include "layout.h"
+
+namespace paig {
+
+// ---------------------------------------------------------------------------------------------------------
+// UNet tables
+// ---------------------------------------------------------------------------------------------------------
+static void add_buf(UNetDesc& u, int C, int shift) { u.bufs[u.nbufs++] = BufDesc{C, shift}; }
+static void add_op(UNetDesc& u, int kind, int layer, Ref in, Ref out, int relu) {
+    u.ops[u.nops++] = Op{kind, layer, in, out, relu};
+}
+
+UNetDesc make_unet(int deep, int n) {
+    UNetDesc u;
+    const Ref X{-1, 0, 3}, LOG{-2, 0, n};
+    if (!deep) {
+        // blocks.py:278-308, hidden 8.  ReLU after every conv except c7 and c10; the 1x1 head keeps its ReLU (Q9).
+        const int h = 8;
+        enum { A1, CATB, P1, A3, CATA, P2, A5, A6, U1, A8, A9, U2, A11, A12 };
+        add_buf(u, h, 0);       // A1   c1
+        add_buf(u, 3 * h, 0);   // CATB [0:16) c10 | [16:24) x1 = c2
+        add_buf(u, h, 1);       // P1
+        add_buf(u, 2 * h, 1);   // A3   c3
+        add_buf(u, 4 * h, 1);   // CATA [0:16) c7 | [16:32) x2 = c4
+        add_buf(u, 2 * h, 2);   // P2
+        add_buf(u, 4 * h, 2);   // A5   c5
+        add_buf(u, 4 * h, 2);   // A6   c6
+        add_buf(u, 4 * h, 1);   // U1
+        add_buf(u, 2 * h, 1);   // A8   c8
+        add_buf(u, 2 * h, 1);   // A9   c9
+        add_buf(u, 2 * h, 0);   // U2
+        add_buf(u, h, 0);       // A11  c11
+        add_buf(u, h, 0);       // A12  c12
+        add_op(u, OP_CONV, 0, X, Ref{A1, 0, h}, 1);
+        add_op(u, OP_CONV, 1, Ref{A1, 0, h}, Ref{CATB, 2 * h, h}, 1);
+        add_op(u, OP_POOL, -1, Ref{CATB, 2 * h, h}, Ref{P1, 0, h}, 0);
+        add_op(u, OP_CONV, 2, Ref{P1, 0, h}, Ref{A3, 0, 2 * h}, 1);
+        add_op(u, OP_CONV, 3, Ref{A3, 0, 2 * h}, Ref{CATA, 2 * h, 2 * h}, 1);
+        add_op(u, OP_POOL, -1, Ref{CATA, 2 * h, 2 * h}, Ref{P2, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 4, Ref{P2, 0, 2 * h}, Ref{A5, 0, 4 * h}, 1);
+        add_op(u, OP_CONV, 5, Ref{A5, 0, 4 * h}, Ref{A6, 0, 4 * h}, 1);
+        add_op(u, OP_UP, -1, Ref{A6, 0, 4 * h}, Ref{U1, 0, 4 * h}, 0);
+        add_op(u, OP_CONV, 6, Ref{U1, 0, 4 * h}, Ref{CATA, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 7, Ref{CATA, 0, 4 * h}, Ref{A8, 0, 2 * h}, 1);
+        add_op(u, OP_CONV, 8, Ref{A8, 0, 2 * h}, Ref{A9, 0, 2 * h}, 1);
+        add_op(u, OP_UP, -1, Ref{A9, 0, 2 * h}, Ref{U2, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 9, Ref{U2, 0, 2 * h}, Ref{CATB, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 10, Ref{CATB, 0, 3 * h}, Ref{A11, 0, h}, 1);
+        add_op(u, OP_CONV, 11, Ref{A11, 0, h}, Ref{A12, 0, h}, 1);
+        add_op(u, OP_HEAD, 12, Ref{A12, 0, h}, LOG, 1);
+        u.logits_relu = 1;
+    } else {
+        // blocks.py:172-237, hidden 16.  No ReLU after c9, c12, c15 and the 1x1 head c18.
+        const int h = 16;
+        enum { A1, CATC, P1, A3, CATB, P2, A5, CATA, P3, A7, A8, U1, A10, A11, U2, A13, A14, U3, A16, A17 };
+        add_buf(u, h, 0);        // A1   c1
+        add_buf(u, 3 * h, 0);    // CATC [0:32) c15 | [32:48) x1 = c2
+        add_buf(u, h, 1);        // P1
+        add_buf(u, 2 * h, 1);    // A3   c3
+        add_buf(u, 4 * h, 1);    // CATB [0:32) c12 | [32:64) x2 = c4
+        add_buf(u, 2 * h, 2);    // P2
+        add_buf(u, 4 * h, 2);    // A5   c5
+        add_buf(u, 6 * h, 2);    // CATA [0:32) c9 | [32:96) x3 = c6
+        add_buf(u, 4 * h, 3);    // P3
+        add_buf(u, 8 * h, 3);    // A7   c7
+        add_buf(u, 8 * h, 3);    // A8   c8
+        add_buf(u, 8 * h, 2);    // U1
+        add_buf(u, 4 * h, 2);    // A10  c10
+        add_buf(u, 4 * h, 2);    // A11  c11
+        add_buf(u, 4 * h, 1);    // U2
+        add_buf(u, 2 * h, 1);    // A13  c13
+        add_buf(u, 2 * h, 1);    // A14  c14
+        add_buf(u, 2 * h, 0);    // U3
+        add_buf(u, h, 0);        // A16  c16
+        add_buf(u, h, 0);        // A17  c17
+        add_op(u, OP_CONV, 0, X, Ref{A1, 0, h}, 1);
+        add_op(u, OP_CONV, 1, Ref{A1, 0, h}, Ref{CATC, 2 * h, h}, 1);
+        add_op(u, OP_POOL, -1, Ref{CATC, 2 * h, h}, Ref{P1, 0, h}, 0);
+        add_op(u, OP_CONV, 2, Ref{P1, 0, h}, Ref{A3, 0, 2 * h}, 1);
+        add_op(u, OP_CONV, 3, Ref{A3, 0, 2 * h}, Ref{CATB, 2 * h, 2 * h}, 1);
+        add_op(u, OP_POOL, -1, Ref{CATB, 2 * h, 2 * h}, Ref{P2, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 4, Ref{P2, 0, 2 * h}, Ref{A5, 0, 4 * h}, 1);
+        add_op(u, OP_CONV, 5, Ref{A5, 0, 4 * h}, Ref{CATA, 2 * h, 4 * h}, 1);
+        add_op(u, OP_POOL, -1, Ref{CATA, 2 * h, 4 * h}, Ref{P3, 0, 4 * h}, 0);
+        add_op(u, OP_CONV, 6, Ref{P3, 0, 4 * h}, Ref{A7, 0, 8 * h}, 1);
+        add_op(u, OP_CONV, 7, Ref{A7, 0, 8 * h}, Ref{A8, 0, 8 * h}, 1);
+        add_op(u, OP_UP, -1, Ref{A8, 0, 8 * h}, Ref{U1, 0, 8 * h}, 0);
+        add_op(u, OP_CONV, 8, Ref{U1, 0, 8 * h}, Ref{CATA, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 9, Ref{CATA, 0, 6 * h}, Ref{A10, 0, 4 * h}, 1);
+        add_op(u, OP_CONV, 10, Ref{A10, 0, 4 * h}, Ref{A11, 0, 4 * h}, 1);
+        add_op(u, OP_UP, -1, Ref{A11, 0, 4 * h}, Ref{U2, 0, 4 * h}, 0);
+        add_op(u, OP_CONV, 11, Ref{U2, 0, 4 * h}, Ref{CATB, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 12, Ref{CATB, 0, 4 * h}, Ref{A13, 0, 2 * h}, 1);
+        add_op(u, OP_CONV, 13, Ref{A13, 0, 2 * h}, Ref{A14, 0, 2 * h}, 1);
+        add_op(u, OP_UP, -1, Ref{A14, 0, 2 * h}, Ref{U3, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 14, Ref{U3, 0, 2 * h}, Ref{CATC, 0, 2 * h}, 0);
+        add_op(u, OP_CONV, 15, Ref{CATC, 0, 3 * h}, Ref{A16, 0, h}, 1);
+        add_op(u, OP_CONV, 16, Ref{A16, 0, h}, Ref{A17, 0, h}, 1);
+        add_op(u, OP_HEAD, 17, Ref{A17, 0, h}, LOG, 0);
+        u.logits_relu = 0;
+    }
+    return u;
+}
+
+Layout make_layout(const paig_task* t, int B) {
+    Layout L;
+    L.d = dims_of(t);
+    const Dims& d = L.d;
+    L.B = B;
+    L.N = B * d.e;
+    L.unet = make_unet(t->deep_unet, d.n);
+    L.K = t->deep_unet ? 3 * (d.H / 2) * (d.H / 2) : 3 * d.HW;
+    size_t off = 0;
+    auto take = [&](size_t floats) {
+        size_t o = off;
+        off += align64(floats);
+        return o;
+    };
+    const size_t N = (size_t)L.N, nN = (size_t)d.n * L.N, nB = (size_t)d.n * B;
+    size_t max_w = 0;
+    for (int i = 0; i < L.unet.nbufs; ++i) {
+        const int S = d.H >> L.unet.bufs[i].shift;
+        const size_t fl = N * L.unet.bufs[i].C * S * S;
+        L.act[i] = take(fl);
+        L.grad[i] = take(fl);
+    }
+    for (int i = 0; i < L.unet.nops; ++i) {
+        const Op& op = L.unet.ops[i];
+        if (op.kind == OP_CONV) {
+            const size_t w = wgrad_partials_floats(op.in.C, op.out.C);
+            max_w = w > max_w ? w : max_w;
+        }
+    }
+    const size_t head = (size_t)592 * (kMaxObjs * 17);
+    max_w = head > max_w ? head : max_w;
+    L.logits = take(N * d.n * d.HW);
+    L.d_logits = take(N * d.n * d.HW);
+    L.masks = take(N * (d.n + 1) * d.HW);
+    L.A = take(nN * L.K);
+    L.dA = take(nN * L.K);
+    L.H1 = take(nN * kHidden); L.H2 = take(nN * kHidden); L.O3 = take(nN * 2);
+    L.dH1 = take(nN * kHidden); L.dH2 = take(nN * kHidden); L.dO3 = take(nN * 2);
+    L.enc_pos = take(N * 2 * d.n);
+    L.d_enc_pos = take(N * 2 * d.n);
+    const int vin = 2 * d.in;
+    L.vin = take(nB * vin); L.v1 = take(nB * kVelHidden); L.v2 = take(nB * kVelHidden); L.vout = take(nB * 2);
+    L.dvin = take(nB * vin); L.dv1 = take(nB * kVelHidden); L.dv2 = take(nB * kVelHidden); L.dvout = take(nB * 2);
+    const size_t seq = (size_t)B * (d.steps + 1) * 4 * d.n;
+    L.seq = take(seq);
+    L.d_seq = take(seq);
+    L.d_state0 = take((size_t)B * 4 * d.n);
+    const size_t CN = (size_t)d.n * d.t * d.t * 4 + 3 * d.HW;
+    L.raw = take(CN); L.consts = take(CN); L.hidden = take(3 * kHidden); L.d_consts = take(CN);
+    L.dec_partials = take(decode_partials_floats(t));
+    L.tmpl_scratch = take(templates_scratch_floats(t));
+    L.sse = take((size_t)B * (d.e + d.steps));
+    L.scales = take(d.e + d.steps);
+    L.losses = take(8);
+    L.dphys = take(8);
+    L.partials = take(max_w);
+    L.frames = take(N * d.CHW);
+    L.x_stage = take((size_t)B * d.T * d.CHW);
+    L.total = off;
+    return L;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// UNet interpreter
+// ---------------------------------------------------------------------------------------------------------
+struct View {
+    float* p;
+    long bs;
+    int S;
+};
+
+static View view_of(const Layout& L, float* ws, const Ref& r, bool grad) {
+    View v;
+    const BufDesc& b = L.unet.bufs[r.buf];
+    v.S = L.d.H >> b.shift;
+    v.bs = (long)b.C * v.S * v.S;
+    v.p = ws + (grad ? L.grad[r.buf] : L.act[r.buf]) + (long)r.c0 * v.S * v.S;
+    return v;
+}
+
+static int unet_forward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, const float* frames,
+                        cudaStream_t st) {
+    const Dims& d = L.d;
+    for (int i = 0; i < L.unet.nops; ++i) {
+        const Op& op = L.unet.ops[i];
+        int rc = 0;
+        if (op.kind == OP_CONV) {
+            ConvArgs a;
+            if (op.in.buf == -1) {
+                a.in = frames; a.in_bs = d.CHW; a.S = d.H;
+            } else {
+                View v = view_of(L, ws, op.in, false);
+                a.in = v.p; a.in_bs = v.bs; a.S = v.S;
+            }
+            View o = view_of(L, ws, op.out, false);
+            a.Cin = op.in.C;
+            a.w = p->conv[op.layer].w; a.b = p->conv[op.layer].b;
+            a.out = o.p; a.out_bs = o.bs; a.Cout = op.out.C;
+            a.N = L.N; a.relu = op.relu;
+            rc = conv3x3(a, st);
+        } else if (op.kind == OP_POOL) {
+            View v = view_of(L, ws, op.in, false), o = view_of(L, ws, op.out, false);
+            rc = maxpool2(v.p, v.bs, o.p, o.bs, op.in.C, o.S, L.N, st);
+        } else if (op.kind == OP_UP) {
+            View v = view_of(L, ws, op.in, false), o = view_of(L, ws, op.out, false);
+            rc = upsample2(v.p, v.bs, o.p, o.bs, op.in.C, v.S, L.N, st);
+        } else {
+            View v = view_of(L, ws, op.in, false);
+            rc = conv1x1_forward(v.p, v.bs, op.in.C, p->conv[op.layer].w, p->conv[op.layer].b, ws + L.logits,
+                                 (long)d.n * d.HW, d.n, d.H, L.N, op.relu, st);
+        }
+        if (rc) return rc;
+    }
+    (void)t;
+    return 0;
+}
+
+static int unet_backward(const paig_params* p, const paig_params* g, const Layout& L, float* ws, const float* frames,
+                         cudaStream_t st) {
+    const Dims& d = L.d;
+    float* partials = ws + L.partials;
+    for (int i = L.unet.nops - 1; i >= 0; --i) {
+        const Op& op = L.unet.ops[i];
+        int rc = 0;
+        if (op.kind == OP_HEAD) {
+            View v = view_of(L, ws, op.in, false), dv = view_of(L, ws, op.in, true);
+            rc = conv1x1_backward(v.p, v.bs, op.in.C, p->conv[op.layer].w, ws + L.d_logits, (long)d.n * d.HW,
+                                  op.relu ? ws + L.logits : nullptr, (long)d.n * d.HW, d.n, d.H, L.N, dv.p, dv.bs,
+                                  g->conv[op.layer].w, g->conv[op.layer].b, partials, st);
+        } else if (op.kind == OP_CONV) {
+            View o = view_of(L, ws, op.out, false), go = view_of(L, ws, op.out, true);
+            WgradArgs w;
+            if (op.in.buf == -1) {
+                w.in = frames; w.in_bs = d.CHW;
+            } else {
+                View v = view_of(L, ws, op.in, false);
+                w.in = v.p; w.in_bs = v.bs;
+            }
+            w.Cin = op.in.C;
+            w.g = go.p; w.g_bs = go.bs; w.Cout = op.out.C;
+            w.act = op.relu ? o.p : nullptr; w.act_bs = o.bs;
+            w.S = o.S; w.N = L.N; w.partials = partials;
+            rc = conv3x3_wgrad(w, g->conv[op.layer].w, g->conv[op.layer].b, st);
+            if (!rc && op.in.buf >= 0) {        // no gradient w.r.t. the input frames
+                View gi = view_of(L, ws, op.in, true);
+                ConvArgs a;
+                a.in = go.p; a.in_bs = go.bs; a.Cin = op.out.C;
+                a.mask = op.relu ? o.p : nullptr; a.mask_bs = o.bs;
+                a.w = p->conv[op.layer].w; a.transposed = 1;
+                a.out = gi.p; a.out_bs = gi.bs; a.Cout = op.in.C;
+                a.S = o.S; a.N = L.N;
+                rc = conv3x3(a, st);
+            }
+        } else if (op.kind == OP_POOL) {
+            View v = view_of(L, ws, op.in, false), gi = view_of(L, ws, op.in, true);
+            View go = view_of(L, ws, op.out, true);
+            rc = maxpool2_backward(v.p, v.bs, go.p, go.bs, gi.p, gi.bs, op.in.C, go.S, L.N, st);
+        } else {
+            View gi = view_of(L, ws, op.in, true), go = view_of(L, ws, op.out, true);
+            rc = upsample2_backward(go.p, go.bs, gi.p, gi.bs, op.in.C, gi.S, L.N, st);
+        }
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// mask softmax + masked objects (blocks.py:84-96) and the position head (blocks.py:101-102)
+// ---------------------------------------------------------------------------------------------------------
+// One thread per pixel (POOL: per 2x2 block).  A[o*N + f][c*KP + pp] = m_o * x_c  (POOL: 2x2 mean of it).
+template <int NOBJ, bool POOL>
+__global__ void __launch_bounds__(256) enc_masks_kernel(const float* __restrict__ logits, const float* __restrict__ x,
+                                                        long x_seq_stride, int fps, int H, int N,
+                                                        float* __restrict__ masks, float* __restrict__ A,
+                                                        float* __restrict__ masked_objs) {
+    const int HW = H * H;
+    const int W2 = POOL ? H / 2 : H, KP = POOL ? HW / 4 : HW;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * KP) return;
+    const int f = (int)(idx / KP), pp = (int)(idx % KP);
+    const float* xf = x + (long)(f / fps) * x_seq_stride + (long)(f % fps) * 3 * HW;
+    float accA[NOBJ][3];
+#pragma unroll
+    for (int o = 0; o < NOBJ; ++o)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) accA[o][c] = 0.f;
+    const int np = POOL ? 4 : 1;
+    for (int s = 0; s < np; ++s) {
+        const int p = POOL ? ((pp / W2) * 2 + (s >> 1)) * H + (pp % W2) * 2 + (s & 1) : pp;
+        float z[NOBJ], m = 1.f;
+#pragma unroll
+        for (int o = 0; o < NOBJ; ++o) {
+            z[o] = logits[((long)f * NOBJ + o) * HW + p];
+            m = fmaxf(m, z[o]);
+        }
+        float den = 0.f, e[NOBJ + 1];
+#pragma unroll
+        for (int o = 0; o < NOBJ; ++o) {
+            e[o] = expf(z[o] - m);
+            den += e[o];
+        }
+        e[NOBJ] = expf(1.f - m);           // background logit: the constant 1 (blocks.py:86)
+        den += e[NOBJ];
+        const float inv = 1.f / den;
+#pragma unroll
+        for (int o = 0; o <= NOBJ; ++o) masks[((long)f * (NOBJ + 1) + o) * HW + p] = e[o] * inv;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float xv = xf[c * HW + p];
+#pragma unroll
+            for (int o = 0; o < NOBJ; ++o) {
+                const float v = e[o] * inv * xv;
+                accA[o][c] += v;
+                if (masked_objs) masked_objs[(((long)o * N + f) * 3 + c) * HW + p] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 0; o < NOBJ; ++o)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            A[((long)o * N + f) * (3 * KP) + c * KP + pp] = POOL ? 0.25f * accA[o][c] : accA[o][c];
+}
+
+// d logits from dA:  dm_o = sum_c dA * x_c (x .25 under the 2x2 mean);  dz_k = m_k (dm_k - sum_j m_j dm_j)
+template <int NOBJ, bool POOL>
+__global__ void __launch_bounds__(256) enc_masks_bwd_kernel(const float* __restrict__ masks, const float* __restrict__ x,
+                                                            long x_seq_stride, int fps, int H, int N,
+                                                            const float* __restrict__ dA, float* __restrict__ d_logits) {
+    const int HW = H * H;
+    const int W2 = POOL ? H / 2 : H, KP = POOL ? HW / 4 : HW;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)N * HW) return;
+    const int f = (int)(idx / HW), p = (int)(idx % HW);
+    const int pp = POOL ? ((p / H) / 2) * W2 + (p % H) / 2 : p;
+    const float* xf = x + (long)(f / fps) * x_seq_stride + (long)(f % fps) * 3 * HW;
+    float dm[NOBJ], mk[NOBJ], dot = 0.f;
+#pragma unroll
+    for (int o = 0; o < NOBJ; ++o) {
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) s += dA[((long)o * N + f) * (3 * KP) + c * KP + pp] * xf[c * HW + p];
+        dm[o] = POOL ? 0.25f * s : s;
+        mk[o] = masks[((long)f * (NOBJ + 1) + o) * HW + p];
+        dot += mk[o] * dm[o];
+    }
+#pragma unroll
+    for (int o = 0; o < NOBJ; ++o) d_logits[((long)f * NOBJ + o) * HW + p] = mk[o] * (dm[o] - dot);
+}
+
+// enc_pos[f, 2o+c] = tanh(O3[o*N+f, c]) * H/2 + H/2      (blocks.py:101-102)
+__global__ void __launch_bounds__(256) pos_head_kernel(const float* __restrict__ O3, int N, int n, float half,
+                                                       float* __restrict__ enc_pos, float* __restrict__ enc_pos2) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * 2 * n) return;
+    const int f = idx / (2 * n), k = idx % (2 * n), o = k >> 1, c = k & 1;
+    const float v = tanhf(O3[((long)o * N + f) * 2 + c]) * half + half;
+    enc_pos[idx] = v;
+    if (enc_pos2) enc_pos2[idx] = v;
+}
+__global__ void __launch_bounds__(256) pos_head_bwd_kernel(const float* __restrict__ O3, int N, int n, float half,
+                                                           const float* __restrict__ d_enc_pos,
+                                                           float* __restrict__ dO3) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * 2 * n) return;
+    const int f = idx / (2 * n), k = idx % (2 * n), o = k >> 1, c = k & 1;
+    const long j = ((long)o * N + f) * 2 + c;
+    const float th = tanhf(O3[j]);
+    dO3[j] = d_enc_pos[idx] * half * (1.f - th * th);
+}
+
+template <int NOBJ>
+static int masks_fwd(const Layout& L, bool pool, float* ws, const float* x, long ss, int fps, float* masks,
+                     float* masked, cudaStream_t st) {
+    const Dims& d = L.d;
+    const long total = (long)L.N * (pool ? d.HW / 4 : d.HW);
+    if (pool)
+        launch(enc_masks_kernel<NOBJ, true>, dim3(cdiv(total, 256)), dim3(256), 0, st, (const float*)(ws + L.logits), x,
+               ss, fps, d.H, L.N, masks, ws + L.A, masked);
+    else
+        launch(enc_masks_kernel<NOBJ, false>, dim3(cdiv(total, 256)), dim3(256), 0, st, (const float*)(ws + L.logits), x,
+               ss, fps, d.H, L.N, masks, ws + L.A, masked);
+    return check_launch("enc_masks");
+}
+template <int NOBJ>
+static int masks_bwd(const Layout& L, bool pool, float* ws, const float* x, long ss, int fps, cudaStream_t st) {
+    const Dims& d = L.d;
+    const long total = (long)L.N * d.HW;
+    if (pool)
+        launch(enc_masks_bwd_kernel<NOBJ, true>, dim3(cdiv(total, 256)), dim3(256), 0, st, (const float*)(ws + L.masks),
+               x, ss, fps, d.H, L.N, (const float*)(ws + L.dA), ws + L.d_logits);
+    else
+        launch(enc_masks_bwd_kernel<NOBJ, false>, dim3(cdiv(total, 256)), dim3(256), 0, st,
+               (const float*)(ws + L.masks), x, ss, fps, d.H, L.N, (const float*)(ws + L.dA), ws + L.d_logits);
+    return check_launch("enc_masks_bwd");
+}
+
+// frames of the encoder batch made contiguous [N,3,H,H]
+__global__ void __launch_bounds__(256) gather_frames_kernel(const float4* __restrict__ x, long seq_stride4, int fps,
+                                                            int chw4, long total4, float4* __restrict__ out) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total4) return;
+    const long f = idx / chw4, r = idx % chw4;
+    out[idx] = x[(f / fps) * seq_stride4 + (f % fps) * chw4 + r];
+}
+
+int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride,
+                    int fps, float* enc_pos_out, float* enc_masks_out, float* masked_out, float* ws, cudaStream_t st) {
+    const Dims& d = L.d;
+    if (L.N <= 0) return 0;
+    // The mask stage indexes frames as x + (f/fps)*seq_stride + (f%fps)*CHW; conv3x3 wants a plain batch stride,
+    // so when the encoded frames are only a prefix of each sequence they are gathered once (kept for backward).
+    const float* frames = x;
+    if (seq_stride != (long)fps * d.CHW) {
+        float* dst = ws + L.frames;
+        const long total4 = (long)L.N * d.CHW / 4;
+        launch(gather_frames_kernel, dim3(cdiv(total4, 256)), dim3(256), 0, st, (const float4*)x, seq_stride / 4, fps,
+               d.CHW / 4, total4, (float4*)dst);
+        int rc0 = check_launch("gather_frames");
+        if (rc0) return rc0;
+        frames = dst;
+    }
+    int rc = unet_forward(t, p, L, ws, frames, st);
+    if (rc) return rc;
+    float* masks = ws + L.masks;
+    switch (d.n) {
+        case 1: rc = masks_fwd<1>(L, t->deep_unet, ws, x, seq_stride, fps, masks, masked_out, st); break;
+        case 2: rc = masks_fwd<2>(L, t->deep_unet, ws, x, seq_stride, fps, masks, masked_out, st); break;
+        default: rc = masks_fwd<3>(L, t->deep_unet, ws, x, seq_stride, fps, masks, masked_out, st); break;
+    }
+    if (rc) return rc;
+    if (enc_masks_out)
+        cudaMemcpyAsync(enc_masks_out, masks, (size_t)L.N * (d.n + 1) * d.HW * sizeof(float), cudaMemcpyDeviceToDevice,
+                        st);
+    const int M = d.n * L.N;
+    if ((rc = linear_forward(ws + L.A, p->enc_l1.w, p->enc_l1.b, ws + L.H1, M, L.K, kHidden, EPI_RELU, st))) return rc;
+    if ((rc = linear_forward(ws + L.H1, p->enc_l2.w, p->enc_l2.b, ws + L.H2, M, kHidden, kHidden, EPI_RELU, st)))
+        return rc;
+    if ((rc = linear_forward(ws + L.H2, p->enc_l3.w, p->enc_l3.b, ws + L.O3, M, kHidden, 2, EPI_NONE, st))) return rc;
+    launch(pos_head_kernel, dim3(cdiv(L.N * 2 * d.n, 256)), dim3(256), 0, st, (const float*)(ws + L.O3), L.N, d.n,
+           (float)d.H * 0.5f, ws + L.enc_pos, enc_pos_out);
+    return check_launch("pos_head");
+}
+
+// d_enc_pos: [N, 2n].  Writes every encoder gradient (UNet convs, l1..l3).
+int encoder_backward(const paig_task* t, const paig_params* p, const paig_params* g, const Layout& L, const float* x,
+                     long seq_stride, int fps, const float* d_enc_pos, float* ws, cudaStream_t st) {
+    const Dims& d = L.d;
+    if (L.N <= 0) return 0;
+    int rc;
+    const int M = d.n * L.N;
+    launch(pos_head_bwd_kernel, dim3(cdiv(L.N * 2 * d.n, 256)), dim3(256), 0, st, (const float*)(ws + L.O3), L.N, d.n,
+           (float)d.H * 0.5f, d_enc_pos, ws + L.dO3);
+    if ((rc = check_launch("pos_head_bwd"))) return rc;
+    // l3
+    if ((rc = linear_wgrad(ws + L.dO3, ws + L.H2, g->enc_l3.w, g->enc_l3.b, M, kHidden, 2, st))) return rc;
+    if ((rc = linear_dgrad(ws + L.dO3, p->enc_l3.w, ws + L.dH2, M, kHidden, 2, EPI_MASK_RELU, ws + L.H2, st))) return rc;
+    // l2
+    if ((rc = linear_wgrad(ws + L.dH2, ws + L.H1, g->enc_l2.w, g->enc_l2.b, M, kHidden, kHidden, st))) return rc;
+    if ((rc = linear_dgrad(ws + L.dH2, p->enc_l2.w, ws + L.dH1, M, kHidden, kHidden, EPI_MASK_RELU, ws + L.H1, st)))
+        return rc;
+    // l1
+    if ((rc = linear_wgrad(ws + L.dH1, ws + L.A, g->enc_l1.w, g->enc_l1.b, M, L.K, kHidden, st))) return rc;
+    if ((rc = linear_dgrad(ws + L.dH1, p->enc_l1.w, ws + L.dA, M, L.K, kHidden, EPI_NONE, nullptr, st))) return rc;
+    switch (d.n) {
+        case 1: rc = masks_bwd<1>(L, t->deep_unet, ws, x, seq_stride, fps, st); break;
+        case 2: rc = masks_bwd<2>(L, t->deep_unet, ws, x, seq_stride, fps, st); break;
+        default: rc = masks_bwd<3>(L, t->deep_unet, ws, x, seq_stride, fps, st); break;
+    }
+    if (rc) return rc;
+    const float* frames = seq_stride != (long)fps * d.CHW ? ws + L.frames : x;   // gathered by encoder_forward
+    return unet_backward(p, g, L, ws, frames, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// VelocityEncoder (blocks.py:31-49) and the initial rollout state (physics_models.py:220-228)
+// ---------------------------------------------------------------------------------------------------------
+// Vin[o*B + b][tau*2 + c] = enc_pos[b, tau, 2o+c]            (alt_vel: difference of consecutive steps)
+__global__ void __launch_bounds__(256) vel_gather_kernel(const float* __restrict__ enc_pos, int B, int n, int e, int in,
+                                                         int alt, float* __restrict__ vin) {
+    const int cols = alt ? 2 * (in - 1) : 2 * in;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * B * cols) return;
+    const int col = idx % cols, row = idx / cols, o = row / B, b = row % B, tau = col >> 1, c = col & 1;
+    const float* ep = enc_pos + ((long)b * e) * 2 * n + 2 * o + c;
+    vin[idx] = alt ? ep[(long)(tau + 1) * 2 * n] - ep[(long)tau * 2 * n] : ep[(long)tau * 2 * n];
+}
+// seq[b, 0, :] = [ enc_pos[b, in-1, :] | vel ]   with vel[b, 2o+c] = vout[o*B+b, c]  (zeros when in == 1)
+__global__ void __launch_bounds__(256) state0_kernel(const float* __restrict__ enc_pos, const float* __restrict__ vout,
+                                                     int B, int n, int e, int in, int steps, float* __restrict__ seq) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * 4 * n) return;
+    const int b = idx / (4 * n), k = idx % (4 * n);
+    float v;
+    if (k < 2 * n) v = enc_pos[((long)b * e + (in - 1)) * 2 * n + k];
+    else {
+        const int kk = k - 2 * n;
+        v = vout ? vout[((long)(kk >> 1) * B + b) * 2 + (kk & 1)] : 0.f;
+    }
+    seq[(long)b * (steps + 1) * 4 * n + k] = v;
+}
+__global__ void __launch_bounds__(256) state0_bwd_kernel(const float* __restrict__ d_state0, int B, int n, int e, int in,
+                                                         float* __restrict__ d_enc_pos, float* __restrict__ dvout) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * 4 * n) return;
+    const int b = idx / (4 * n), k = idx % (4 * n);
+    const float v = d_state0[idx];
+    if (k < 2 * n) d_enc_pos[((long)b * e + (in - 1)) * 2 * n + k] += v;
+    else if (dvout) {
+        const int kk = k - 2 * n;
+        dvout[((long)(kk >> 1) * B + b) * 2 + (kk & 1)] = v;
+    }
+}
+// adjoint of vel_gather: one thread per (b, o, c) walks tau, so no atomics
+__global__ void __launch_bounds__(256) vel_scatter_kernel(const float* __restrict__ dvin, int B, int n, int e, int in,
+                                                          int alt, float* __restrict__ d_enc_pos) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * 2 * n) return;
+    const int b = idx / (2 * n), k = idx % (2 * n), o = k >> 1, c = k & 1;
+    const int cols = alt ? 2 * (in - 1) : 2 * in;
+    const float* dv = dvin + ((long)o * B + b) * cols + c;
+    float* dp = d_enc_pos + ((long)b * e) * 2 * n + k;
+    if (alt) {
+        for (int tau = 0; tau < in - 1; ++tau) {
+            const float v = dv[2 * tau];
+            dp[(long)(tau + 1) * 2 * n] += v;
+            dp[(long)tau * 2 * n] -= v;
+        }
+    } else {
+        for (int tau = 0; tau < in; ++tau) dp[(long)tau * 2 * n] += dv[2 * tau];
+    }
+}
+
+int velocity_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* enc_pos, float* ws,
+                     cudaStream_t st) {
+    const Dims& d = L.d;
+    if (L.B <= 0) return 0;
+    int rc = 0;
+    const float* vout = nullptr;
+    if (d.in > 1) {                                                   // physics_models.py:220-223
+        const int M = d.n * L.B, cols = t->alt_vel ? 2 * (d.in - 1) : 2 * d.in;
+        launch(vel_gather_kernel, dim3(cdiv(M * cols, 256)), dim3(256), 0, st, enc_pos, L.B, d.n, d.e, d.in,
+               (int)t->alt_vel, ws + L.vin);
+        if ((rc = check_launch("vel_gather"))) return rc;
+        if (t->alt_vel) {
+            rc = linear_forward(ws + L.vin, p->vel[0].w, p->vel[0].b, ws + L.vout, M, cols, 2, EPI_NONE, st);
+        } else {
+            rc = linear_forward(ws + L.vin, p->vel[0].w, p->vel[0].b, ws + L.v1, M, cols, kVelHidden, EPI_TANH, st);
+            if (!rc) rc = linear_forward(ws + L.v1, p->vel[1].w, p->vel[1].b, ws + L.v2, M, kVelHidden, kVelHidden, EPI_TANH, st);
+            if (!rc) rc = linear_forward(ws + L.v2, p->vel[2].w, p->vel[2].b, ws + L.vout, M, kVelHidden, 2, EPI_NONE, st);
+        }
+        if (rc) return rc;
+        vout = ws + L.vout;
+    }
+    launch(state0_kernel, dim3(cdiv(L.B * 4 * d.n, 256)), dim3(256), 0, st, enc_pos, vout, L.B, d.n, d.e, d.in, d.steps,
+           ws + L.seq);
+    return check_launch("state0");
+}
+
+// d_state0 [B,4n] -> accumulates into d_enc_pos [B,e,2n]; writes the velocity-encoder gradients.
+int velocity_backward(const paig_task* t, const paig_params* p, const paig_params* g, const Layout& L,
+                      const float* d_state0, float* d_enc_pos, float* ws, cudaStream_t st) {
+    const Dims& d = L.d;
+    if (L.B <= 0) return 0;
+    int rc;
+    const bool has_vel = d.in > 1;
+    launch(state0_bwd_kernel, dim3(cdiv(L.B * 4 * d.n, 256)), dim3(256), 0, st, d_state0, L.B, d.n, d.e, d.in, d_enc_pos,
+           has_vel ? ws + L.dvout : (float*)nullptr);
+    if ((rc = check_launch("state0_bwd"))) return rc;
+    if (!has_vel) return 0;
+    const int M = d.n * L.B, cols = t->alt_vel ? 2 * (d.in - 1) : 2 * d.in;
+    if (t->alt_vel) {
+        if ((rc = linear_wgrad(ws + L.dvout, ws + L.vin, g->vel[0].w, g->vel[0].b, M, cols, 2, st))) return rc;
+        if ((rc = linear_dgrad(ws + L.dvout, p->vel[0].w, ws + L.dvin, M, cols, 2, EPI_NONE, nullptr, st))) return rc;
+    } else {
+        if ((rc = linear_wgrad(ws + L.dvout, ws + L.v2, g->vel[2].w, g->vel[2].b, M, kVelHidden, 2, st))) return rc;
+        if ((rc = linear_dgrad(ws + L.dvout, p->vel[2].w, ws + L.dv2, M, kVelHidden, 2, EPI_MASK_TANH, ws + L.v2, st)))
+            return rc;
+        if ((rc = linear_wgrad(ws + L.dv2, ws + L.v1, g->vel[1].w, g->vel[1].b, M, kVelHidden, kVelHidden, st))) return rc;
+        if ((rc = linear_dgrad(ws + L.dv2, p->vel[1].w, ws + L.dv1, M, kVelHidden, kVelHidden, EPI_MASK_TANH, ws + L.v1,
+                               st)))
+            return rc;
+        if ((rc = linear_wgrad(ws + L.dv1, ws + L.vin, g->vel[0].w, g->vel[0].b, M, cols, kVelHidden, st))) return rc;
+        if ((rc = linear_dgrad(ws + L.dv1, p->vel[0].w, ws + L.dvin, M, cols, kVelHidden, EPI_NONE, nullptr, st)))
+            return rc;
+    }
+    launch(vel_scatter_kernel, dim3(cdiv(L.B * 2 * d.n, 256)), dim3(256), 0, st, (const float*)(ws + L.dvin), L.B, d.n,
+           d.e, d.in, (int)t->alt_vel, d_enc_pos);
+    return check_launch("vel_scatter");
+}
+
+}  // namespace paig

@@ -4,6 +4,8 @@
 
 namespace paig {
 
+bool valid_task(const paig_task* t);
+
 // rollout.cu
 int rollout_forward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1, float* seq,
                     cudaStream_t st);
@@ -36,6 +38,43 @@ int templates_forward(const paig_task* t, const paig_params* p, float* raw, floa
 int templates_backward(const paig_task* t, const paig_params* p, const paig_params* g, const float* consts,
                        const float* hidden, const float* d_consts, float* scratch, cudaStream_t st);
 size_t templates_scratch_floats(const paig_task* t);
+
+// conv.cu -- all tensors are channel-sliced NCHW views: (n,c,y,x) = p[n*bs + (c*S + y)*S + x]
+struct ConvArgs {
+    const float* in = nullptr; long in_bs = 0; int Cin = 0;
+    const float* mask = nullptr; long mask_bs = 0;    // nullable: input is multiplied by (mask > 0)  (ReLU adjoint)
+    const float* w = nullptr;                          // [Cout][Cin][3][3]; transposed: layer weight [Cin][Cout][3][3], taps flipped
+    const float* b = nullptr;                          // nullable
+    float* out = nullptr; long out_bs = 0; int Cout = 0;
+    int S = 0, N = 0;
+    int relu = 0, transposed = 0;
+    int QX = 0, TH = 0, FPB = 0;                       // filled by conv3x3()
+};
+int conv3x3(const ConvArgs& a, cudaStream_t st);
+constexpr int kWgradMaxCtas = 296;
+struct WgradArgs {
+    const float* in = nullptr; long in_bs = 0; int Cin = 0;       // layer input
+    const float* in_mask = nullptr; long in_mask_bs = 0;          // nullable
+    const float* g = nullptr; long g_bs = 0; int Cout = 0;        // gradient of the layer's (post-ReLU) output
+    const float* act = nullptr; long act_bs = 0;                  // nullable: layer output, for the ReLU mask
+    int S = 0, N = 0;
+    float* partials = nullptr;                                    // >= wgrad_partials_floats(Cin, Cout)
+    int in_plane = 0, g_plane = 0;                                // filled by conv3x3_wgrad()
+};
+int conv3x3_wgrad(const WgradArgs& a, float* dW, float* db, cudaStream_t st);
+size_t wgrad_partials_floats(int Cin, int Cout);
+int reduce_partials(const float* partials, int nparts, int stride, int n0, float* out0, int n1, float* out1,
+                    cudaStream_t st);
+int conv1x1_forward(const float* in, long in_bs, int Cin, const float* w, const float* b, float* out, long out_bs,
+                    int Cout, int S, int N, int relu, cudaStream_t st);
+int conv1x1_backward(const float* in, long in_bs, int Cin, const float* w, const float* dout, long dout_bs,
+                     const float* act, long act_bs, int Cout, int S, int N, float* din, long din_bs, float* dW,
+                     float* db, float* partials, cudaStream_t st);
+int maxpool2(const float* in, long in_bs, float* out, long out_bs, int C, int So, int N, cudaStream_t st);
+int maxpool2_backward(const float* in, long in_bs, const float* dout, long dout_bs, float* din, long din_bs, int C,
+                      int So, int N, cudaStream_t st);
+int upsample2(const float* in, long in_bs, float* out, long out_bs, int C, int Si, int N, cudaStream_t st);
+int upsample2_backward(const float* dout, long dout_bs, float* din, long din_bs, int C, int Si, int N, cudaStream_t st);
 
 // gemm.cu
 enum { EPI_NONE = 0, EPI_RELU = 1, EPI_TANH = 2, EPI_MASK_RELU = 3, EPI_MASK_TANH = 4 };

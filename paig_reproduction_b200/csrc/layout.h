@@ -1,0 +1,66 @@
+// Workspace layout of one training step.  The caller owns the buffer (paig_workspace_bytes); this header
+// only assigns offsets (in floats, each region 256-byte aligned) so forward and backward agree on them.
+#pragma once
+#include "common.cuh"
+#include "internal.h"
+
+namespace paig {
+
+// ---- UNet description (blocks.py:106-308) as data: buffers + a forward op list ------------------
+enum OpKind { OP_CONV = 0, OP_POOL = 1, OP_UP = 2, OP_HEAD = 3 };
+struct Ref {
+    int buf;   // >= 0: UNet buffer index; -1: the input frames; -2: the logits
+    int c0;    // first channel of the slice
+    int C;     // channels in the slice
+};
+struct Op {
+    int kind;
+    int layer;   // conv index (0-based into paig_params.conv) for OP_CONV / OP_HEAD
+    Ref in, out;
+    int relu;
+};
+struct BufDesc {
+    int C;       // total channels
+    int shift;   // spatial side = H >> shift
+};
+constexpr int kMaxBufs = 24, kMaxOps = 32;
+struct UNetDesc {
+    int nbufs = 0, nops = 0;
+    BufDesc bufs[kMaxBufs];
+    Op ops[kMaxOps];
+    int logits_relu = 0;
+};
+UNetDesc make_unet(int deep, int n_objs);
+
+inline size_t align64(size_t floats) { return (floats + 63) & ~(size_t)63; }
+
+struct Layout {
+    Dims d;
+    int B = 0, N = 0;            // local sequences, encoded frames (B * (in+pr))
+    int K = 0;                   // encoder.l1 in_features (blocks.py:70-73)
+    UNetDesc unet;
+    size_t act[kMaxBufs], grad[kMaxBufs];
+    size_t logits, d_logits, masks, A, dA, H1, H2, O3, dH1, dH2, dO3, enc_pos, d_enc_pos;
+    size_t vin, v1, v2, vout, dvin, dv1, dv2, dvout;
+    size_t seq, d_seq, d_state0;
+    size_t raw, consts, hidden, d_consts, dec_partials, tmpl_scratch;
+    size_t sse, scales, losses, dphys;
+    size_t partials;             // conv wgrad / head partial sums
+    size_t frames;               // gathered encoder frames [N,3,H,H] (when they are a prefix of each sequence)
+    size_t x_stage;              // device copy of the input for the *_host entry point
+    size_t total;
+};
+
+Layout make_layout(const paig_task* t, int B);
+
+// encoder.cu
+int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride,
+                    int fps, float* enc_pos_out, float* enc_masks_out, float* masked_out, float* ws, cudaStream_t st);
+int encoder_backward(const paig_task* t, const paig_params* p, const paig_params* g, const Layout& L, const float* x,
+                     long seq_stride, int fps, const float* d_enc_pos, float* ws, cudaStream_t st);
+int velocity_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* enc_pos, float* ws,
+                     cudaStream_t st);
+int velocity_backward(const paig_task* t, const paig_params* p, const paig_params* g, const Layout& L,
+                      const float* d_state0, float* d_enc_pos, float* ws, cudaStream_t st);
+
+}  // namespace paig

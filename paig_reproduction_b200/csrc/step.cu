@@ -1,0 +1,350 @@
+// The whole PhysicsNet step: conv_feedforward (physics_models.py:204-245) + compute_loss (:119-142) and the
+// backward pass autograd would run (base.py:151), as a fixed sequence of kernel launches on one stream.
+//
+//   forward : templates -> encoder -> velocity -> rollout -> decode(recons + rollout frames) -> losses
+//   backward: decode^T (in the same kernel as decode when the loss gradient is formed in-kernel)
+//             -> rollout^T -> velocity^T -> encoder^T -> templates^T
+#include "common.cuh"
+#include "internal.h"
+#include "layout.h"
+
+#include <cstring>
+
+namespace paig {
+
+// scales[0:e) = alpha/(Bg*e) recons weights ; scales[e:e+steps) = 1/(Bg*pr) for s < pr, else 0
+__global__ void loss_scales_kernel(float* __restrict__ scales, int e, int steps, int pr, float alpha, float Bg) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e) scales[i] = alpha > 0.f ? alpha / (Bg * (float)e) : 0.f;
+    else if (i < e + steps) scales[i] = (i - e) < pr ? 1.f / (Bg * (float)pr) : 0.f;
+}
+
+// losses = [train, pred, extrap, recons]  (physics_models.py:122-141; means over the GLOBAL batch, so
+// data-parallel shards sum to the job's loss).  One block, fixed order.
+__global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ sse, int B, int e, int steps, int pr,
+                                                            float alpha, float Bg, float* __restrict__ losses) {
+    __shared__ float scratch[33];
+    float r = 0.f, p = 0.f, x = 0.f;
+    for (int i = threadIdx.x; i < B * e; i += blockDim.x) r += sse[i];
+    const float* s2 = sse + (long)B * e;
+    for (int i = threadIdx.x; i < B * steps; i += blockDim.x) {
+        if (i % steps < pr) p += s2[i];
+        else x += s2[i];
+    }
+    r = block_sum(r, scratch);
+    p = block_sum(p, scratch);
+    x = block_sum(x, scratch);
+    if (threadIdx.x == 0) {
+        const float recons = r / (Bg * (float)e), pred = p / (Bg * (float)pr);
+        const int ex = steps - pr;
+        const float extrap = ex > 0 ? x / (Bg * (float)ex) : 0.f;
+        losses[0] = alpha > 0.f ? pred + alpha * recons : pred;
+        losses[1] = pred;
+        losses[2] = extrap;
+        losses[3] = recons;
+    }
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ y, const float* __restrict__ x, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
+static float batch_global(const paig_task* t, int B) { return (float)(t->batch_global > 0 ? t->batch_global : B); }
+
+static void segments(const paig_task* t, const Layout& L, float* ws, const float* x, DecSeg* A, DecSeg* R) {
+    const Dims& d = L.d;
+    A->nframes = L.B * d.e;
+    A->fps = d.e;
+    A->loc = ws + L.enc_pos;
+    A->loc_row_stride = 2 * d.n;
+    A->loc_seq_stride = (long)d.e * 2 * d.n;
+    A->target = x;
+    A->tgt_seq_stride = (long)d.T * d.CHW;
+    A->sse = ws + L.sse;
+    R->nframes = L.B * d.steps;
+    R->fps = d.steps;
+    R->loc = ws + L.seq + 4 * d.n;                    // row s+1 of pos_vel_seq holds the state decoded as frame s
+    R->loc_row_stride = 4 * d.n;
+    R->loc_seq_stride = (long)(d.steps + 1) * 4 * d.n;
+    R->target = x + (long)d.in * d.CHW;
+    R->tgt_seq_stride = (long)d.T * d.CHW;
+    R->sse = ws + L.sse + (long)L.B * d.e;
+    (void)t;
+}
+
+static int forward_common(const paig_task* t, const paig_params* p, const Layout& L, const float* x,
+                          const paig_outputs* out, float* ws, cudaStream_t st) {
+    const Dims& d = L.d;
+    int rc;
+    if ((rc = templates_forward(t, p, out && out->templates ? out->templates : ws + L.raw, ws + L.consts,
+                                ws + L.hidden, st)))
+        return rc;
+    if ((rc = encoder_forward(t, p, L, x, (long)d.T * d.CHW, d.e, out ? out->enc_pos : nullptr,
+                              out ? out->enc_masks : nullptr, out ? out->masked_objs : nullptr, ws, st)))
+        return rc;
+    if ((rc = velocity_forward(t, p, L, ws + L.enc_pos, ws, st))) return rc;
+    if ((rc = rollout_forward(t->cell, d.n, L.B, d.steps, p->dt, p->phys0, p->phys1, ws + L.seq, st))) return rc;
+    if (out && out->pos_vel_seq)
+        cudaMemcpyAsync(out->pos_vel_seq, ws + L.seq, (size_t)L.B * (d.steps + 1) * 4 * d.n * sizeof(float),
+                        cudaMemcpyDeviceToDevice, st);
+    return 0;
+}
+
+static int finalize_losses(const paig_task* t, const Layout& L, float* ws, float* losses_out, cudaStream_t st) {
+    const Dims& d = L.d;
+    launch(loss_finalize_kernel, dim3(1), dim3(256), 0, st, (const float*)(ws + L.sse), L.B, d.e, d.steps, d.pr,
+           t->alpha, batch_global(t, L.B), ws + L.losses);
+    int rc = check_launch("loss_finalize");
+    if (rc) return rc;
+    if (losses_out) cudaMemcpyAsync(losses_out, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    return 0;
+}
+
+int step_forward(const paig_task* t, const paig_params* p, const float* x, int B, const paig_outputs* out, float* ws,
+                 cudaStream_t st) {
+    const Layout L = make_layout(t, B);
+    int rc = forward_common(t, p, L, x, out, ws, st);
+    if (rc) return rc;
+    DecSeg A, R;
+    segments(t, L, ws, x, &A, &R);
+    A.frames = out ? out->recons_out : nullptr;
+    R.frames = out ? out->output_seq : nullptr;
+    if ((rc = decode_run(t, ws + L.consts, A, R, false, nullptr, nullptr, 0, st))) return rc;
+    return finalize_losses(t, L, ws, out ? out->losses : nullptr, st);
+}
+
+// Everything after the decoder's backward: d_seq / d_enc_pos / d_consts are complete in the workspace.
+static int backward_tail(const paig_task* t, const paig_params* p, const paig_params* g, const Layout& L,
+                         const float* x, float* ws, cudaStream_t st) {
+    const Dims& d = L.d;
+    int rc;
+    double* dphys = reinterpret_cast<double*>(ws + L.dphys);
+    const long rs = 4L * d.n;
+    if ((rc = rollout_backward(t->cell, d.n, L.B, d.steps, p->dt, p->phys0, p->phys1, ws + L.seq, ws + L.d_seq,
+                               ws + L.d_seq + 2 * d.n, (d.steps + 1) * rs, rs, 1, ws + L.d_state0, dphys, st)))
+        return rc;
+    if (t->cell != PAIG_CELL_BOUNCING) {
+        if (g->phys0) cudaMemcpyAsync(g->phys0, dphys, sizeof(double), cudaMemcpyDeviceToDevice, st);
+        if (t->cell == PAIG_CELL_SPRING && g->phys1)
+            cudaMemcpyAsync(g->phys1, dphys + 1, sizeof(double), cudaMemcpyDeviceToDevice, st);
+    }
+    if ((rc = velocity_backward(t, p, g, L, ws + L.d_state0, ws + L.d_enc_pos, ws, st))) return rc;
+    if ((rc = encoder_backward(t, p, g, L, x, (long)d.T * d.CHW, d.e, ws + L.d_enc_pos, ws, st))) return rc;
+    return templates_backward(t, p, g, ws + L.consts, ws + L.hidden, ws + L.d_consts, ws + L.tmpl_scratch, st);
+}
+
+static void route_dloc(const Layout& L, float* ws, DecSeg* A, DecSeg* R) {
+    const Dims& d = L.d;
+    A->dloc = ws + L.d_enc_pos;
+    A->dloc_row_stride = A->loc_row_stride;
+    A->dloc_seq_stride = A->loc_seq_stride;
+    R->dloc = ws + L.d_seq + 4 * d.n;                 // position half of rows 1..steps of d(pos_vel_seq)
+    R->dloc_row_stride = R->loc_row_stride;
+    R->dloc_seq_stride = R->loc_seq_stride;
+}
+
+int step_backward(const paig_task* t, const paig_params* p, const paig_params* g, const float* x, int B,
+                  const float* d_output_seq, const float* d_recons_out, const float* d_enc_pos,
+                  const float* d_pos_vel_seq, float* ws, cudaStream_t st) {
+    const Layout L = make_layout(t, B);
+    const Dims& d = L.d;
+    const size_t seq_fl = (size_t)B * (d.steps + 1) * 4 * d.n, ep_fl = (size_t)L.N * 2 * d.n;
+    cudaMemsetAsync(ws + L.d_seq, 0, seq_fl * sizeof(float), st);
+    cudaMemsetAsync(ws + L.d_enc_pos, 0, ep_fl * sizeof(float), st);
+    DecSeg A, R, none;
+    segments(t, L, ws, x, &A, &R);
+    route_dloc(L, ws, &A, &R);
+    A.target = R.target = nullptr;                    // gradients come from memory; losses were done in forward
+    A.sse = R.sse = nullptr;
+    A.dframes = d_recons_out;
+    R.dframes = d_output_seq;
+    if (!d_recons_out) A = none;                      // STALE mode: that branch receives no gradient
+    if (!d_output_seq) R = none;
+    int rc;
+    const size_t CN = (size_t)d.n * d.t * d.t * 4 + 3 * d.HW;
+    if (A.nframes + R.nframes > 0) {
+        if ((rc = decode_run(t, ws + L.consts, A.nframes ? A : R, A.nframes ? R : none, true, ws + L.dec_partials,
+                             ws + L.d_consts, 0, st)))
+            return rc;
+    } else {
+        cudaMemsetAsync(ws + L.d_consts, 0, CN * sizeof(float), st);
+    }
+    if (d_enc_pos) {
+        launch(axpy_kernel, dim3(cdiv(ep_fl, 256)), dim3(256), 0, st, ws + L.d_enc_pos, d_enc_pos, (long)ep_fl);
+        if ((rc = check_launch("axpy"))) return rc;
+    }
+    if (d_pos_vel_seq) {
+        launch(axpy_kernel, dim3(cdiv(seq_fl, 256)), dim3(256), 0, st, ws + L.d_seq, d_pos_vel_seq, (long)seq_fl);
+        if ((rc = check_launch("axpy"))) return rc;
+    }
+    return backward_tail(t, p, g, L, x, ws, st);
+}
+
+int step_fused(const paig_task* t, const paig_params* p, const paig_params* g, const float* x, int B,
+               const paig_outputs* out, float* ws, cudaStream_t st) {
+    const Layout L = make_layout(t, B);
+    const Dims& d = L.d;
+    int rc = forward_common(t, p, L, x, out, ws, st);
+    if (rc) return rc;
+    launch(loss_scales_kernel, dim3(1), dim3(256), 0, st, ws + L.scales, d.e, d.steps, d.pr, t->alpha,
+           batch_global(t, B));
+    if ((rc = check_launch("loss_scales"))) return rc;
+    cudaMemsetAsync(ws + L.d_seq, 0, (size_t)B * (d.steps + 1) * 4 * d.n * sizeof(float), st);
+    DecSeg A, R;
+    segments(t, L, ws, x, &A, &R);
+    route_dloc(L, ws, &A, &R);
+    A.scale = ws + L.scales;
+    R.scale = ws + L.scales + d.e;
+    A.frames = out ? out->recons_out : nullptr;       // normally NULL: the fused step never writes frames
+    R.frames = out ? out->output_seq : nullptr;
+    if ((rc = decode_run(t, ws + L.consts, A, R, true, ws + L.dec_partials, ws + L.d_consts, 0, st))) return rc;
+    if ((rc = finalize_losses(t, L, ws, out ? out->losses : nullptr, st))) return rc;
+    return backward_tail(t, p, g, L, x, ws, st);
+}
+
+}  // namespace paig
+
+using namespace paig;
+
+extern "C" {
+
+size_t paig_workspace_bytes(const paig_task* t, int B) {
+    if (!t || B < 0 || t->n_objs < 1 || t->n_objs > kMaxObjs || t->H < 8 || t->seq_len <= t->input_steps + t->pred_steps) {
+        set_error("paig_workspace_bytes: invalid task");
+        return 0;
+    }
+    return make_layout(t, B > 0 ? B : 1).total * sizeof(float);
+}
+
+int paig_step_forward(const paig_task* t, const paig_params* p, const float* x, int B, const paig_outputs* out,
+                      void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    return step_forward(t, p, x, B, out, (float*)workspace, (cudaStream_t)stream);
+}
+
+int paig_step_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x, int B,
+                       const float* d_output_seq, const float* d_recons_out, const float* d_enc_pos,
+                       const float* d_pos_vel_seq, void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    return step_backward(t, p, grads, x, B, d_output_seq, d_recons_out, d_enc_pos, d_pos_vel_seq, (float*)workspace,
+                         (cudaStream_t)stream);
+}
+
+int paig_step_fused(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x, int B,
+                    const paig_outputs* out, void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    return step_fused(t, p, grads, x, B, out, (float*)workspace, (cudaStream_t)stream);
+}
+
+int paig_step_fused_host(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x_host, int B,
+                         float* losses_host, void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    const Layout L = make_layout(t, B);
+    float* ws = (float*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemcpyAsync(ws + L.x_stage, x_host, (size_t)B * L.d.T * L.d.CHW * sizeof(float), cudaMemcpyHostToDevice, st);
+    int rc = step_fused(t, p, grads, ws + L.x_stage, B, nullptr, ws, st);
+    if (rc) return rc;
+    cudaMemcpyAsync(losses_host, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    return check_launch("step_fused_host");
+}
+
+int paig_encoder_forward(const paig_task* t, const paig_params* p, const float* x, long seq_stride, int frames_per_seq,
+                         int N, float* enc_pos, float* enc_masks, float* masked_objs, void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    if (N % (t->input_steps + t->pred_steps) != 0) {
+        set_error("encoder: N=%d must be a multiple of input_steps+pred_steps", N);
+        return 1;
+    }
+    const Layout L = make_layout(t, N / (t->input_steps + t->pred_steps));
+    return encoder_forward(t, p, L, x, seq_stride, frames_per_seq, enc_pos, enc_masks, masked_objs, (float*)workspace,
+                           (cudaStream_t)stream);
+}
+
+int paig_encoder_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x,
+                          long seq_stride, int frames_per_seq, int N, const float* d_enc_pos, void* workspace,
+                          void* stream) {
+    if (!valid_task(t)) return 1;
+    const Layout L = make_layout(t, N / (t->input_steps + t->pred_steps));
+    return encoder_backward(t, p, grads, L, x, seq_stride, frames_per_seq, d_enc_pos, (float*)workspace,
+                            (cudaStream_t)stream);
+}
+
+int paig_velocity_forward(const paig_task* t, const paig_params* p, const float* enc_pos, int B, float* vel,
+                          void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    const Layout L = make_layout(t, B);
+    float* ws = (float*)workspace;
+    int rc = velocity_forward(t, p, L, enc_pos, ws, (cudaStream_t)stream);
+    if (rc) return rc;
+    // vel [B, 2n] = velocity half of row 0 of the rollout state
+    const Dims& d = L.d;
+    if (vel) {
+        // strided copy: row 0 of sequence b starts at seq + b*(steps+1)*4n; take columns [2n, 4n)
+        cudaMemcpy2DAsync(vel, 2 * d.n * sizeof(float), ws + L.seq + 2 * d.n, (size_t)(d.steps + 1) * 4 * d.n * sizeof(float),
+                          2 * d.n * sizeof(float), B, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+    }
+    return check_launch("velocity_forward");
+}
+
+int paig_velocity_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* enc_pos,
+                           int B, const float* d_vel, float* d_enc_pos_accum, void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    (void)enc_pos;
+    const Layout L = make_layout(t, B);
+    const Dims& d = L.d;
+    float* ws = (float*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    // d_state0 = [0 | d_vel]
+    cudaMemsetAsync(ws + L.d_state0, 0, (size_t)B * 4 * d.n * sizeof(float), st);
+    cudaMemcpy2DAsync(ws + L.d_state0 + 2 * d.n, 4 * d.n * sizeof(float), d_vel, 2 * d.n * sizeof(float),
+                      2 * d.n * sizeof(float), B, cudaMemcpyDeviceToDevice, st);
+    return velocity_backward(t, p, grads, L, ws + L.d_state0, d_enc_pos_accum, ws, st);
+}
+
+long paig_debug_workspace_offset(const paig_task* t, int B, const char* region, int index) {
+    if (!valid_task(t) || !region) return -1;
+    const Layout L = make_layout(t, B);
+    auto is = [&](const char* n) { return strcmp(region, n) == 0; };
+    if (is("act") || is("grad")) {
+        if (index < 0 || index >= L.unet.nbufs) return -1;
+        return (long)(is("act") ? L.act[index] : L.grad[index]);
+    }
+    if (is("logits")) return (long)L.logits;
+    if (is("d_logits")) return (long)L.d_logits;
+    if (is("enc_pos")) return (long)L.enc_pos;
+    if (is("d_enc_pos")) return (long)L.d_enc_pos;
+    if (is("seq")) return (long)L.seq;
+    if (is("d_seq")) return (long)L.d_seq;
+    if (is("consts")) return (long)L.consts;
+    if (is("d_consts")) return (long)L.d_consts;
+    if (is("H1")) return (long)L.H1;
+    if (is("H2")) return (long)L.H2;
+    if (is("A")) return (long)L.A;
+    if (is("dA")) return (long)L.dA;
+    return -1;
+}
+
+int paig_debug_unet_conv_view(const paig_task* t, int B, int layer, long view[5]) {
+    if (!valid_task(t) || !view) return 1;
+    const Layout L = make_layout(t, B);
+    for (int i = 0; i < L.unet.nops; ++i) {
+        const Op& op = L.unet.ops[i];
+        if ((op.kind != OP_CONV && op.kind != OP_HEAD) || op.layer != layer) continue;
+        if (op.kind == OP_HEAD) {
+            view[0] = (long)L.logits; view[1] = (long)L.d.n * L.d.HW; view[2] = L.d.n; view[3] = L.d.H;
+        } else {
+            const BufDesc& b = L.unet.bufs[op.out.buf];
+            const int S = L.d.H >> b.shift;
+            view[0] = (long)L.act[op.out.buf] + (long)op.out.c0 * S * S;
+            view[1] = (long)b.C * S * S; view[2] = op.out.C; view[3] = S;
+        }
+        view[4] = op.relu;
+        return 0;
+    }
+    set_error("no conv layer %d", layer);
+    return 1;
+}
+
+}  // extern "C"

@@ -132,6 +132,11 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
     memmove(d, s, n);
     return 0;
 }
+static inline cudaError_t cudaMemcpy2DAsync(void* d, size_t dpitch, const void* s, size_t spitch, size_t width,
+                                            size_t height, cudaMemcpyKind, cudaStream_t = 0) {
+    for (size_t r = 0; r < height; ++r) memmove((char*)d + r * dpitch, (const char*)s + r * spitch, width);
+    return 0;
+}
 template <typename F>
 static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return 0; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
