@@ -159,6 +159,13 @@ int paig_velocity_forward(const paig_task* t, const paig_params* p, const float*
 int paig_velocity_backward(const paig_task* t, const paig_params* p, const paig_params* grads, const float* enc_pos,
                            int B, const float* d_vel, float* d_enc_pos_accum, void* workspace, void* stream);
 
+/* compute_loss's per-frame squared error (physics_models.py:122-131) for the drop-in compute_loss():
+ * sse[b,f] = sum_chw (x[b, first+f] - pred[b,f])^2, and d_pred = 2 * d_sse[b,f] * (pred - x). */
+int paig_frame_sse_forward(const float* x, long x_seq_stride, int first, const float* pred, int B, int F, int chw,
+                           float* sse, void* stream);
+int paig_frame_sse_backward(const float* x, long x_seq_stride, int first, const float* pred, int B, int F, int chw,
+                            const float* d_sse, float* d_pred, void* stream);
+
 /* ---- layer primitives (exported for unit tests of the encoder's building blocks) ------------------- */
 
 /* nn.Conv2d(Cin, Cout, 3, padding="same") (+ReLU) on x [N,Cin,S,S] -> y [N,Cout,S,S]   (blocks.py:246-276) */
@@ -168,6 +175,12 @@ int paig_conv3x3_forward(const float* x, const float* w, const float* b, float* 
  * workspace: at least 296 * (Cout*Cin*9 + Cout) floats. */
 int paig_conv3x3_backward(const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
                           float* db, int N, int Cin, int Cout, int S, int relu, void* workspace, void* stream);
+
+/* Measurement hooks (bench.py): cumulative number of kernels this library launched; per-launch CUDA-event
+ * timing between begin/end, reported as "kernel-name launches total_ms" lines. */
+long paig_launch_count(void);
+void paig_profile_begin(void);
+int paig_profile_end(char* buf, size_t cap);
 
 /* Test hook: offset (in floats) of a named workspace region ("act", "grad" with a UNet buffer index; "logits",
  * "d_logits", "enc_pos", "d_enc_pos", "seq", "d_seq", "d_consts", "consts", "A", "dA"), or -1. */

@@ -91,6 +91,11 @@ def declare(lib):
         "paig_encoder_backward": (i, [PT, PP, PP, vp, l, i, i, vp, vp, vp]),
         "paig_velocity_forward": (i, [PT, PP, vp, i, vp, vp, vp]),
         "paig_velocity_backward": (i, [PT, PP, PP, vp, i, vp, vp, vp, vp]),
+        "paig_launch_count": (C.c_long, []),
+        "paig_profile_begin": (None, []),
+        "paig_profile_end": (i, [C.c_char_p, C.c_size_t]),
+        "paig_frame_sse_forward": (i, [vp, l, i, vp, i, i, i, vp, vp]),
+        "paig_frame_sse_backward": (i, [vp, l, i, vp, i, i, i, vp, vp, vp]),
         "paig_debug_workspace_offset": (C.c_long, [PT, i, C.c_char_p, i]),
         "paig_debug_unet_conv_view": (i, [PT, i, i, C.POINTER(C.c_long * 5)]),
         "paig_conv3x3_forward": (i, [vp, vp, vp, vp, i, i, i, i, i, vp]),
@@ -112,4 +117,6 @@ EXPORTS = ["paig_abi_version", "paig_last_error", "paig_workspace_bytes", "paig_
            "paig_step_fused", "paig_step_fused_host", "paig_rollout_forward", "paig_rollout_backward",
            "paig_templates_forward", "paig_templates_backward", "paig_decode_forward", "paig_decode_backward",
            "paig_encoder_forward", "paig_encoder_backward", "paig_velocity_forward", "paig_velocity_backward",
-           "paig_conv3x3_forward", "paig_conv3x3_backward", "paig_debug_workspace_offset", "paig_debug_unet_conv_view"]
+           "paig_conv3x3_forward", "paig_conv3x3_backward", "paig_debug_workspace_offset", "paig_debug_unet_conv_view",
+           "paig_frame_sse_forward", "paig_frame_sse_backward", "paig_launch_count", "paig_profile_begin",
+           "paig_profile_end"]

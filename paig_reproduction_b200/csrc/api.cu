@@ -1,6 +1,10 @@
 // extern "C" surface of libpaig_b200.so (declared in include/paig_b200.h).
 #include "internal.h"
 
+#include <map>
+#include <string>
+#include <vector>
+
 namespace paig {
 
 static thread_local char g_err[512] = "";
@@ -12,7 +16,43 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+long g_launch_count = 0;
+bool g_profiling = false;
+
+#ifndef PAIG_EMU
+struct ProfRec {
+    cudaEvent_t a, b;
+    const char* name;
+};
+static std::vector<ProfRec> g_recs;
+static std::vector<cudaEvent_t> g_event_pool;
+static cudaEvent_t take_event() {
+    cudaEvent_t e;
+    if (!g_event_pool.empty()) {
+        e = g_event_pool.back();
+        g_event_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+void prof_before(cudaStream_t st) {
+    ProfRec r{take_event(), take_event(), nullptr};
+    cudaEventRecord(r.a, st);
+    g_recs.push_back(r);
+}
+void prof_after(cudaStream_t st) { cudaEventRecord(g_recs.back().b, st); }
+static void prof_name(const char* what) {
+    if (g_profiling && !g_recs.empty() && g_recs.back().name == nullptr) g_recs.back().name = what;
+}
+#else
+void prof_before(cudaStream_t) {}
+void prof_after(cudaStream_t) {}
+static void prof_name(const char*) {}
+#endif
+
 int check_launch(const char* what) {
+    prof_name(what);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("%s: %s", what, cudaGetErrorString(e));
@@ -45,6 +85,49 @@ extern "C" {
 int paig_abi_version(void) { return PAIG_ABI_VERSION; }
 
 const char* paig_last_error(void) { return g_err; }
+
+long paig_launch_count(void) { return g_launch_count; }
+
+void paig_profile_begin(void) {
+#ifndef PAIG_EMU
+    g_recs.clear();
+    g_profiling = true;
+#endif
+}
+
+/* Stops per-launch timing, waits for the device and writes "name launches total_ms" lines into buf. */
+int paig_profile_end(char* buf, size_t cap) {
+#ifndef PAIG_EMU
+    g_profiling = false;
+    if (cudaDeviceSynchronize() != cudaSuccess) {
+        set_error("profile_end: %s", cudaGetErrorString(cudaGetLastError()));
+        return 2;
+    }
+    std::map<std::string, std::pair<long, double>> agg;
+    for (auto& r : g_recs) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        auto& e = agg[r.name ? r.name : "?"];
+        e.first += 1;
+        e.second += ms;
+        g_event_pool.push_back(r.a);
+        g_event_pool.push_back(r.b);
+    }
+    g_recs.clear();
+    std::string out;
+    for (auto& kv : agg) {
+        char line[256];
+        snprintf(line, sizeof(line), "%s %ld %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && cap) {
+        snprintf(buf, cap, "%s", out.c_str());
+    }
+#else
+    if (buf && cap) buf[0] = 0;
+#endif
+    return 0;
+}
 
 int paig_rollout_forward(int cell, int n_objs, int B, int steps, const float* dt, const double* phys0,
                          const double* phys1, float* pos_vel_seq, void* stream) {

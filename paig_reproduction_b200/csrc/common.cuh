@@ -40,6 +40,13 @@ inline Dims dims_of(const paig_task* k) {
     return d;
 }
 
+// launch accounting / optional per-launch CUDA-event timing (api.cu); used by bench.py for "gpu_launches" and for
+// the live per-kernel durations behind its roofline line
+extern long g_launch_count;
+extern bool g_profiling;
+void prof_before(cudaStream_t st);
+void prof_after(cudaStream_t st);
+
 // Kernel launch through a function pointer so the same call compiles for the GPU and for tests/emu.
 template <typename... KArgs, typename... Args>
 inline void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
@@ -48,7 +55,10 @@ inline void launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, c
     emu::launch(grid, block, smem, [&]() { kern(KArgs(args)...); });
 #else
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    ++g_launch_count;
+    if (g_profiling) prof_before(stream);
     kern<<<grid, block, smem, stream>>>(KArgs(args)...);
+    if (g_profiling) prof_after(stream);
 #endif
 }
 

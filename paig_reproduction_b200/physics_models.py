@@ -1,0 +1,390 @@
+"""Drop-in PhysicsNet whose per-sequence training step runs in libpaig_b200.so (hand-written sm_100a kernels).
+
+Mirrors the Python surface of the reference's ``nn/network/physics_models.py:PhysicsNet`` (constructor
+argument order, ``forward`` / ``conv_feedforward`` / ``compute_loss`` / ``build_optimizer``, the cached
+attributes and every ``state_dict`` key), so ``runners/torch_run_physics.py`` can construct it unchanged.
+The parameters live in ordinary ``nn.Module`` holders (same construction order as the reference, hence the
+same default initialisation under the same seed), but no torch operator runs on the hot path: ``forward``
+is one call into the C ABI (include/paig_b200.h), wrapped in one ``torch.autograd.Function``.
+
+There is no CPU path and no PyTorch fallback: tensors must be CUDA tensors and the library must load.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _abi, _lib
+
+# physics_models.py:31-37
+COORD_UNITS = {"bouncing_balls": 8, "spring_color": 8, "spring_color_half": 8, "3bp_color": 12,
+               "mnist_spring_color": 8}
+# cells.py class names accepted by the runner's --cell_type table (runners/torch_run_physics.py:49-75)
+CELLS = {"spring_ode_cell": "spring", "bouncing_ode_cell": "bouncing", "gravity_ode_cell": "gravity"}
+# base.py:12-17
+OPTIMIZERS = {"adam": torch.optim.Adam, "rmsprop": torch.optim.RMSprop, "momentum": lambda p, lr: torch.optim.SGD(p, lr, momentum=0.9),
+              "sgd": torch.optim.SGD}
+
+
+# ---- parameter holders (never executed with torch ops; they exist for state_dict / optimizer parity) ----
+class VariableFromNetwork(nn.Module):
+    """blocks.py:311-322."""
+
+    def __init__(self, shape):
+        super().__init__()
+        self.shape = list(shape)
+        self.l1 = nn.Linear(10, 200)
+        self.l2 = nn.Linear(200, int(np.prod(shape)))
+
+
+def _conv(cin, cout, k=3):
+    return nn.Conv2d(cin, cout, kernel_size=k, padding="same")
+
+
+class ShallowUNet(nn.Module):
+    """blocks.py:240-276 (layer shapes only)."""
+
+    def __init__(self, in_channels, h, out_features):
+        super().__init__()
+        chans = [(in_channels, h), (h, h), (h, 2 * h), (2 * h, 2 * h), (2 * h, 4 * h), (4 * h, 4 * h), (4 * h, 2 * h),
+                 (4 * h, 2 * h), (2 * h, 2 * h), (2 * h, 2 * h), (3 * h, h), (h, h)]
+        for i, (ci, co) in enumerate(chans, start=1):
+            setattr(self, "c%d" % i, _conv(ci, co))
+        self.c13 = _conv(h, out_features, 1)
+
+
+class UNet(nn.Module):
+    """blocks.py:106-170 (layer shapes only)."""
+
+    def __init__(self, in_channels, h, out_features):
+        super().__init__()
+        chans = [(in_channels, h), (h, h), (h, 2 * h), (2 * h, 2 * h), (2 * h, 4 * h), (4 * h, 4 * h), (4 * h, 8 * h),
+                 (8 * h, 8 * h), (8 * h, 2 * h), (6 * h, 4 * h), (4 * h, 4 * h), (4 * h, 2 * h), (4 * h, 2 * h),
+                 (2 * h, 2 * h), (2 * h, 2 * h), (3 * h, h), (h, h)]
+        for i, (ci, co) in enumerate(chans, start=1):
+            setattr(self, "c%d" % i, _conv(ci, co))
+        self.c18 = _conv(h, out_features, 1)
+
+
+class ConvolutionalEncoder(nn.Module):
+    """blocks.py:52-75: both UNets are always constructed; only one is used."""
+
+    def __init__(self, in_features, hidden_dim, out_features, n_objects):
+        super().__init__()
+        c, h, _ = in_features
+        self.shallow_unet = ShallowUNet(c, 8, n_objects)
+        self.unet = UNet(c, 16, n_objects)
+        l1_in = h * h * c if h < 40 else (h // 2) * (h // 2) * c
+        self.l1 = nn.Linear(l1_in, hidden_dim)
+        self.l2 = nn.Linear(hidden_dim, hidden_dim)
+        self.l3 = nn.Linear(hidden_dim, out_features)
+
+
+class VelocityEncoder(nn.Module):
+    """blocks.py:8-29."""
+
+    def __init__(self, alt_vel, input_steps, n_objs, coord_units):
+        super().__init__()
+        if alt_vel:
+            self.init_vel_linear = nn.Linear((input_steps - 1) * 2, 2)
+        else:
+            self.init_vel_mlp = nn.Sequential(nn.Linear(input_steps * coord_units // n_objs // 2, 100), nn.Tanh(),
+                                              nn.Linear(100, 100), nn.Tanh(),
+                                              nn.Linear(100, coord_units // n_objs // 2))
+
+
+class ODECell(nn.RNNCell):
+    """cells.py:6-8,24-29,55-58,87-94: an RNNCell subclass, so it carries the (dead) weight_ih/hh, bias_ih/hh."""
+
+    def __init__(self, kind, size):
+        super().__init__(size, size)
+        self.kind = kind
+        self.dt = nn.Parameter(torch.tensor(0.5 if kind == "gravity" else 0.3), requires_grad=False)
+        if kind == "spring":
+            self.k = nn.Parameter(torch.tensor(np.log(1.0)), requires_grad=True)           # float64, as the reference
+            self.equil = nn.Parameter(torch.tensor(np.log(1.0)), requires_grad=True)
+        elif kind == "gravity":
+            self.g = nn.Parameter(torch.tensor(np.log(1.0)), requires_grad=True)
+            self.m = nn.Parameter(torch.tensor(np.log(1.0)), requires_grad=False)
+            # the reference caches A = exp(g) exp(2m) here once; the kernels recompute it every step
+
+
+class _Step(torch.autograd.Function):
+    """conv_feedforward as one autograd node: forward = paig_step_forward, backward = paig_step_backward."""
+
+    @staticmethod
+    def forward(ctx, net, inp, need_backward, *params):
+        out = net._run_forward(inp, need_backward=need_backward)
+        ctx.net = net
+        ctx.inp = inp
+        ctx.ws = out.pop("_workspace")
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(out["enc_masks"], out["masked_objs"])
+        net._last = out
+        return out["output_seq"], out["recons_out"], out["enc_pos"], out["pos_vel_seq"], out["enc_masks"], out["masked_objs"]
+
+    @staticmethod
+    def backward(ctx, d_out, d_rec, d_enc_pos, d_seq, _dm, _dmo):
+        grads = ctx.net._run_backward(ctx.inp, ctx.ws, d_out, d_rec, d_enc_pos, d_seq)
+        return (None, None, None) + tuple(grads)
+
+
+class PhysicsNet(nn.Module):
+    """physics_models.py:40-111.  Same positional constructor as the reference."""
+
+    def __init__(self, task="", recurrent_units=128, lstm_layers=1, cell_type="", seq_len=20, input_steps=3,
+                 pred_steps=5, autoencoder_loss=0.0, alt_vel=False, color=False, input_size=36 * 36,
+                 encoder_type="conv_encoder", decoder_type="conv_st_decoder", device="cuda"):
+        super().__init__()
+        assert task in COORD_UNITS                                   # physics_models.py:84
+        if cell_type not in CELLS:
+            raise KeyError(cell_type)                                # the reference looks the class up by name (:75-77)
+        if decoder_type != "conv_st_decoder" or encoder_type != "conv_encoder":
+            raise KeyError("%s / %s" % (encoder_type, decoder_type))
+        if not color:
+            # torch.tile(template, [1,3,1,1]) hard-codes 3 channels: grayscale is broken in the reference
+            raise NotImplementedError("only --color configurations are supported (as in the reference, SURVEY Q12)")
+        self.device = torch.device(device)
+        self.task = task
+        self.recurrent_units, self.lstm_layers = recurrent_units, lstm_layers
+        self.cell_kind = CELLS[cell_type]
+        self.seq_len, self.input_steps, self.pred_steps = seq_len, input_steps, pred_steps
+        assert seq_len > input_steps + pred_steps and input_steps >= 1 and pred_steps >= 1       # :59,85-86
+        self.extrap_steps = seq_len - input_steps - pred_steps
+        self.autoencoder_loss = autoencoder_loss
+        self.alt_vel = bool(alt_vel)
+        self.color = color
+        self.input_size = input_size
+        side = int(np.sqrt(input_size))
+        self.conv_ch = 3
+        self.input_shape = [3, side, side]
+        self.conv_input_shape = [3, side, side]
+        self.coord_units = COORD_UNITS[task]
+        self.n_objs = self.coord_units // 4
+        self.log_sig = 1.0
+        self.extra_valid_fns, self.extra_test_fns = [], []
+        tmpl = side // 2
+        # construction order = the reference's (physics_models.py:106-111): same default init under the same seed
+        self.var_net_content = VariableFromNetwork([self.n_objs, 3, tmpl, tmpl])
+        self.var_net_background = VariableFromNetwork([1, 3, side, side])
+        self.var_net_template = VariableFromNetwork([self.n_objs, 1, tmpl, tmpl])
+        self.encoder = ConvolutionalEncoder(self.conv_input_shape, 200, 2, self.n_objs)
+        self.velocity_encoder = VelocityEncoder(self.alt_vel, input_steps, self.n_objs, self.coord_units)
+        self.rollout_cell = ODECell(self.cell_kind, self.coord_units // 2)
+        self.to(self.device)
+
+        self.H = side
+        self.deep = side >= 40                                       # blocks.py:79-82
+        self._unet = "unet" if self.deep else "shallow_unet"
+        self._n_convs = 18 if self.deep else 13
+        self.batch_global = 0           # set by the data-parallel wrapper: loss normalisers use the job's batch
+        self._ws_nograd: Dict[int, torch.Tensor] = {}
+        self._last: Optional[dict] = None
+        self._flat_grad: Optional[torch.Tensor] = None
+        self.optimizer = None
+
+    # ------------------------------------------------------------------ C-ABI plumbing
+    def _task(self, T: int) -> _abi.Task:
+        return _abi.Task(_abi.CELL_IDS[self.cell_kind], self.n_objs, self.H, T, self.input_steps, self.pred_steps,
+                         int(self.alt_vel), int(self.deep), float(self.autoencoder_loss), int(self.batch_global))
+
+    def live_parameter_names(self, with_rollout: bool = True) -> List[str]:
+        """state_dict keys that receive a gradient in a LIVE step, in state_dict order."""
+        names = []
+        for k, _ in self.named_parameters():
+            if k.startswith("encoder.") and not (k.startswith("encoder." + self._unet + ".") or k.startswith("encoder.l")):
+                continue                                              # the unused UNet
+            if k.startswith("rollout_cell."):
+                if not with_rollout or k.rsplit(".", 1)[1] not in ("k", "equil", "g"):
+                    continue                                          # RNNCell weights, dt, m
+            if k.startswith("velocity_encoder.") and not with_rollout:
+                continue
+            names.append(k)
+        return names
+
+    def _param_table(self, tensors: Dict[str, torch.Tensor]) -> _abi.Params:
+        p = _abi.Params()
+        for t in tensors.values():
+            if not (t.is_cuda and t.is_contiguous()):
+                raise _lib.PaigError("parameters must be contiguous CUDA tensors (no CPU path exists)")
+        _abi.fill_params(p, lambda k: tensors[k].data_ptr(), tensors.keys(), self._unet, self._n_convs, self.alt_vel,
+                         self.cell_kind)
+        return p
+
+    def _params_now(self) -> Dict[str, torch.Tensor]:
+        return {k: v.data for k, v in self.named_parameters()}
+
+    def _workspace(self, T: int, B: int, fresh: bool) -> torch.Tensor:
+        lib = _lib.load()
+        tk = self._task(T)
+        n = lib.paig_workspace_bytes(ctypes.byref(tk), B)
+        if n == 0:
+            raise _lib.PaigError(lib.paig_last_error().decode())
+        key = (T, B)
+        if fresh:
+            return torch.empty(n // 4 + 64, dtype=torch.float32, device=self.device)
+        ws = self._ws_nograd.get(key)
+        if ws is None:
+            ws = self._ws_nograd[key] = torch.empty(n // 4 + 64, dtype=torch.float32, device=self.device)
+        return ws
+
+    def _check_input(self, inp: torch.Tensor):
+        if not inp.is_cuda:
+            raise _lib.PaigError("PhysicsNet (B200) needs CUDA input tensors: there is no CPU fallback")
+        if inp.dim() != 5 or inp.shape[2] != 3 or inp.shape[3] != self.H or inp.shape[4] != self.H:
+            raise ValueError("expected input [B, T, 3, %d, %d], got %s" % (self.H, self.H, tuple(inp.shape)))
+        if inp.shape[1] <= self.input_steps + self.pred_steps:
+            raise ValueError("sequence too short")
+
+    def _run_forward(self, inp: torch.Tensor, need_backward: bool) -> dict:
+        lib = _lib.load()
+        x = inp.detach().contiguous().float()
+        B, T = x.shape[0], x.shape[1]
+        n, H, e, steps = self.n_objs, self.H, self.input_steps + self.pred_steps, T - self.input_steps
+        dev = self.device
+        ws = self._workspace(T, B, fresh=need_backward)
+        out = dict(output_seq=torch.empty(B, steps, 3, H, H, device=dev), recons_out=torch.empty(B, e, 3, H, H, device=dev),
+                   enc_pos=torch.empty(B, e, 2 * n, device=dev), pos_vel_seq=torch.empty(B, steps + 1, 4 * n, device=dev),
+                   enc_masks=torch.empty(B * e, n + 1, H, H, device=dev),
+                   masked_objs=torch.empty(n, B * e, 3, H, H, device=dev),
+                   templates=torch.empty(n * (H // 2) ** 2 * 4 + 3 * H * H, device=dev), losses=torch.empty(4, device=dev))
+        O = _abi.Outputs(*[out[k].data_ptr() for k in ("output_seq", "recons_out", "enc_pos", "pos_vel_seq", "enc_masks",
+                                                       "masked_objs", "templates", "losses")])
+        tk = self._task(T)
+        params = self._params_now()
+        P = self._param_table(params)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.paig_step_forward(ctypes.byref(tk), ctypes.byref(P), x.data_ptr(), B, ctypes.byref(O),
+                                         ws.data_ptr(), stream), "paig_step_forward")
+        out["_workspace"] = ws
+        out["_x"] = x
+        return out
+
+    def _run_backward(self, inp, ws, d_out, d_rec, d_enc_pos, d_seq):
+        lib = _lib.load()
+        x = inp.detach().contiguous().float()
+        B, T = x.shape[0], x.shape[1]
+        with_rollout = d_out is not None or d_seq is not None
+        live = self.live_parameter_names(with_rollout=True)
+        params = self._params_now()
+        grads = {k: torch.empty_like(params[k]) for k in live}
+        P, G = self._param_table(params), self._param_table(grads)
+        tk = self._task(T)
+
+        def ptr(t):
+            return None if t is None else t.contiguous().float().data_ptr()
+        keep = [t.contiguous().float() if t is not None else None for t in (d_out, d_rec, d_enc_pos, d_seq)]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(lib.paig_step_backward(ctypes.byref(tk), ctypes.byref(P), ctypes.byref(G), x.data_ptr(), B,
+                                          *[None if t is None else t.data_ptr() for t in keep], ws.data_ptr(), stream),
+                   "paig_step_backward")
+        result = []
+        for k, p in self.named_parameters():
+            g = grads.get(k)
+            if g is not None and not with_rollout and (k.startswith("velocity_encoder.") or k.startswith("rollout_cell.")):
+                g = None                 # STALE mode: nothing flows through the rollout, grads stay None
+            result.append(g)
+        return result
+
+    # ------------------------------------------------------------------ reference surface
+    def forward(self, input):                                         # physics_models.py:201-202
+        return self.conv_feedforward(input)
+
+    def conv_feedforward(self, inp):                                  # physics_models.py:204-245
+        self._check_input(inp)
+        self.input = inp
+        params = [p for _, p in self.named_parameters()]
+        output_seq, recons_out, enc_pos, pos_vel_seq, enc_masks, masked = _Step.apply(self, inp, torch.is_grad_enabled(), *params)
+        last = self._last
+        self.recons_out = recons_out
+        self.enc_pos = enc_pos
+        self.pos_vel_seq = pos_vel_seq
+        self.enc_masks = enc_masks
+        self.masked_objs = [masked[o] for o in range(self.n_objs)]
+        n, t, H = self.n_objs, self.H // 2, self.H
+        raw = last["templates"]
+        self.template = raw[:n * t * t].view(n, 1, t, t)
+        self.contents = raw[n * t * t:4 * n * t * t].view(n, 3, t, t)
+        self.background_content = torch.sigmoid(raw[4 * n * t * t:].view(1, 3, H, H))
+        self.step_losses = last["losses"]          # [train, pred, extrap, recons] reduced in-kernel (no autograd)
+        return output_seq
+
+    def compute_loss(self):                                           # physics_models.py:119-142
+        from .losses import frame_sse
+        e, i, p = self.input_steps + self.pred_steps, self.input_steps, self.pred_steps
+        x = self.input.detach()
+        Bg = self.batch_global or x.shape[0]
+        scale = float(x.shape[0]) / Bg                                # shards of a data-parallel job sum to the job's mean
+        recons = frame_sse(x, 0, e, self.recons_out)                  # [B, e]
+        self.recons_loss = torch.mean(recons) * scale
+        loss = frame_sse(x, i, x.shape[1] - i, self.output)           # [B, T-in]
+        self.pred_loss = torch.mean(loss[:, :p]) * scale
+        self.extrap_loss = torch.mean(loss[:, p:]) * scale
+        train_loss = self.pred_loss
+        if self.autoencoder_loss > 0.0:
+            train_loss += self.autoencoder_loss * self.recons_loss    # in place, as the reference
+        eval_losses = [self.pred_loss, self.extrap_loss, self.recons_loss]
+        return train_loss, eval_losses
+
+    def build_optimizer(self, base_lr, optimizer="rmsprop", anneal_lr=True):     # physics_models.py:144-149
+        self.base_lr = base_lr
+        self.anneal_lr = anneal_lr
+        self.lr = base_lr
+        self.optimizer = OPTIMIZERS[optimizer](self.parameters(), self.lr)
+
+    def get_batch(self, batch_size, iterator):                        # physics_models.py:113-117
+        batch_x, _ = iterator.next_batch(batch_size)
+        return {"input": batch_x}, (batch_x, None)
+
+    # ------------------------------------------------------------------ fused LIVE step (the fast path)
+    def flat_gradients(self) -> torch.Tensor:
+        """One contiguous fp32 buffer holding the gradient of every live fp32 parameter (+ the 4 loss scalars at the
+        end), so a data-parallel job needs a single all-reduce.  ``p.grad`` of each parameter is a view into it."""
+        if self._flat_grad is None:
+            params = dict(self.named_parameters())
+            names = [k for k in self.live_parameter_names() if params[k].dtype == torch.float32]
+            total = sum(params[k].numel() for k in names)
+            total_al = (total + 3) // 4 * 4
+            flat = torch.zeros(total_al + 4, dtype=torch.float32, device=self.device)
+            off = 0
+            self._grad_views = {}
+            for k in names:
+                n = params[k].numel()
+                self._grad_views[k] = flat[off:off + n].view_as(params[k])
+                off += n
+            self._loss_view = flat[total_al:total_al + 4]
+            self._phys_grad = torch.zeros(2, dtype=torch.float64, device=self.device)
+            i = 0
+            for k in self.live_parameter_names():
+                if params[k].dtype == torch.float64:
+                    self._grad_views[k] = self._phys_grad[i].view(())
+                    i += 1
+            self._flat_grad = flat
+        return self._flat_grad
+
+    def train_step(self, inp: torch.Tensor) -> torch.Tensor:
+        """LIVE step in one library call (paig_step_fused): forward, losses and every parameter gradient.
+        Sets ``p.grad`` (views into ``flat_gradients()``) and returns the device tensor
+        [train, pred, extrap, recons]; the caller runs ``optimizer.step()``.  No frames are materialised."""
+        self._check_input(inp)
+        lib = _lib.load()
+        x = inp.detach().contiguous().float()
+        B, T = x.shape[0], x.shape[1]
+        self.flat_gradients()
+        params = self._params_now()
+        P, G = self._param_table(params), self._param_table(self._grad_views)
+        tk = self._task(T)
+        ws = self._workspace(T, B, fresh=False)
+        O = _abi.Outputs(None, None, None, None, None, None, None, self._loss_view.data_ptr())
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(lib.paig_step_fused(ctypes.byref(tk), ctypes.byref(P), ctypes.byref(G), x.data_ptr(), B,
+                                       ctypes.byref(O), ws.data_ptr(), stream), "paig_step_fused")
+        for k, p in self.named_parameters():
+            v = self._grad_views.get(k)
+            if v is not None:
+                p.grad = v
+        return self._loss_view

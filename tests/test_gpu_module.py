@@ -1,0 +1,147 @@
+"""The drop-in PhysicsNet on a B200 against (a) the golden outputs of the UNMODIFIED reference
+(tests/golden/*.npz, written by oracle/make_golden.py) and (b) the oracle, through the reference's own call
+sequence: net.output = net(inp); loss, evals = net.compute_loss(); loss.backward()."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import physicsnet_oracle as po
+from oracle.make_golden import CASES, grad_digest
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _net(task, T, alpha, alt_vel=False):
+    from paig_reproduction_b200.physics_models import PhysicsNet
+    spec = po.TASKS[task]
+    return PhysicsNet(task, 100, 1, po.CELL_TYPE_NAMES[spec.cell], T, spec.input_steps, spec.pred_steps, alpha, alt_vel,
+                      True, spec.H * spec.H, "conv_encoder", "conv_st_decoder", device=DEV)
+
+
+def _close(a, b, rtol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+    assert err <= rtol, "max-abs-diff / max-abs = %.3e > %.1e" % (err, rtol)
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_matches_reference_goldens(golden_dir, case):
+    """Same weights / inputs as oracle/make_golden.py fed to the reference; compare with what the reference produced."""
+    name, task, batch, seq_len, seed, alpha, alt_vel, mode = case
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    spec = po.TASKS[task]
+    T = seq_len or spec.seq_len
+    net = _net(task, T, alpha, alt_vel)
+    net.load_state_dict(po.init_state_dict(spec, seed, alt_vel), strict=True)
+    x = po.synthetic_frames(spec, batch, T, seed).to(DEV)
+    gravity = spec.cell == "gravity"            # chaotic: see tests/test_gpu_stages.py
+    if mode == "train":
+        net.train()
+        inp = x.clone().requires_grad_(True)                          # base.py:141
+        net.output = net(inp)                                         # LIVE mode (base.py:195)
+        train, (pred_alias, extrap, recons) = net.compute_loss()
+        assert pred_alias is train                                    # the in-place alias of the reference (Q4)
+        train.backward()
+    else:
+        net.eval()
+        with torch.no_grad():
+            net.output = net.conv_feedforward(x)
+            train, (pred_alias, extrap, recons) = net.compute_loss()
+    pred = (train - alpha * recons) if alpha > 0 else train
+    got = np.array([train.item(), pred.item(), extrap.item(), recons.item()])
+    _close(got, gold["losses"], 1e-3 if gravity else 2e-5)
+    _close(net.enc_pos.detach().cpu().numpy(), gold["enc_pos"], 2e-5)
+    _close(net.pos_vel_seq.detach().cpu().numpy(), gold["pos_vel_seq"], 2e-3 if gravity else 5e-5)
+    _close(net.output.detach().cpu()[:, :, :, ::3, ::3].numpy(), gold["output_sub"], 1e-2 if gravity else 5e-5)
+    _close(net.recons_out.detach().cpu()[:, :, :, ::3, ::3].numpy(), gold["recons_sub"], 5e-5)
+    _close(net.output.detach().cpu().double().sum((2, 3, 4)).numpy(), gold["output_sum"], 1e-3 if gravity else 5e-5)
+    _close(net.enc_masks.detach().cpu()[:, :, ::4, ::4].numpy(), gold["enc_masks_sub"], 2e-5)
+    _close(net.template.detach().cpu().numpy(), gold["template"], 1e-5)
+    gold_grads = sorted(k[5:] for k in gold.files if k.startswith("grad/"))
+    if mode == "train":
+        live = sorted(k for k, p in net.named_parameters() if p.grad is not None)
+        assert live == gold_grads                                     # same set of live parameters (Q1 / Q6)
+        for k, p in net.named_parameters():
+            if p.grad is not None:
+                # digests (sum, L2 norm, 48 samples) vs the reference's autograd; a ReLU decision that flips within
+                # rounding noise moves single-pixel contributions (tests/stage_checks.py), hence 1e-3 here and the
+                # kink-aligned 1e-4 bound in test_gpu_stages.py
+                _close(grad_digest(p.grad.detach().cpu()), gold["grad/" + k], 5e-2 if gravity else 1e-3)
+    else:
+        assert all(p.grad is None for p in net.parameters())
+
+
+def test_stale_mode_matches_reference_semantics():
+    """The shipped train loop (base.py:142-143) never refreshes self.output: pred_loss is computed against a stale
+    no-grad tensor, so only the reconstruction path trains and velocity / physics grads stay None."""
+    spec = po.TASKS["spring_color"]
+    alpha, B = 3.0, 3
+    sd = po.init_state_dict(spec, 0)
+    x = po.synthetic_frames(spec, B, spec.seq_len, 0)
+    net = _net("spring_color", spec.seq_len, alpha)
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        net.output = net(x.to(DEV))                                   # what eval_performance leaves behind
+    net(x.to(DEV).requires_grad_(True))                               # train_model: result discarded
+    train, _ = net.compute_loss()
+    train.backward()
+    grads = {k: p.grad for k, p in net.named_parameters()}
+    for k in grads:
+        if k.startswith("velocity_encoder.") or k.startswith("rollout_cell."):
+            assert grads[k] is None, k
+    # oracle with the prediction branch detached
+    leaves = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k not in ("rollout_cell.dt", "rollout_cell.m"))
+              for k, v in sd.items()}
+    ff = po.feedforward(leaves, x, spec)
+    ff["output"] = ff["output"].detach()
+    po.losses(x, ff, spec, alpha)["train"].backward()
+    for k, v in leaves.items():
+        if v.grad is not None and not (k.startswith("velocity_encoder.") or k.startswith("rollout_cell.")):
+            _close(grads[k].cpu().numpy(), v.grad.numpy(), 1e-4)
+
+
+def test_fused_train_step_equals_drop_in_path_and_state_dict_round_trip(tmp_path):
+    spec = po.TASKS["bouncing_balls"]
+    alpha, B = 2.0, 5
+    x = po.synthetic_frames(spec, B, spec.seq_len, 4).to(DEV)
+    torch.manual_seed(1)
+    net = _net("bouncing_balls", spec.seq_len, alpha)                 # default (reference) initialisation
+    net.output = net(x.clone().requires_grad_(True))
+    train, evals = net.compute_loss()
+    train.backward()
+    ref = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+    ref_losses = [train.item(), evals[1].item(), evals[2].item()]
+    torch.save(net.state_dict(), tmp_path / "model.ckpt")              # base.py:167-169 format
+    net2 = _net("bouncing_balls", spec.seq_len, alpha)
+    net2.load_state_dict(torch.load(tmp_path / "model.ckpt"))
+    losses = net2.train_step(x).cpu()
+    assert np.allclose([losses[0], losses[2], losses[3]], ref_losses, rtol=2e-6)
+    got = {k: p.grad for k, p in net2.named_parameters() if p.grad is not None}
+    assert sorted(got) == sorted(ref)
+    for k in ref:
+        _close(got[k].cpu().numpy(), ref[k].cpu().numpy(), 2e-5)
+    # optimizer interop: grads are views of one flat buffer
+    net2.build_optimizer(3e-4, "rmsprop")
+    before = net2.encoder.l3.weight.detach().clone()
+    net2.optimizer.step()
+    assert not torch.equal(before, net2.encoder.l3.weight.detach())
+
+
+def test_eval_batch_sweep_properties():
+    """BASELINE config 5 shape: test-mode rollout (T=30, no_grad).  Size-independent properties at a larger batch:
+    per-sequence independence (a sequence decodes the same alone or inside a batch of 512) and determinism."""
+    spec = po.TASKS["spring_color_half"]
+    net = _net("spring_color_half", 30, 3.0)
+    net.load_state_dict(po.init_state_dict(spec, 0), strict=True)
+    x = po.synthetic_frames(spec, 512, 30, 7).to(DEV)
+    with torch.no_grad():
+        big = net(x).clone()
+        pv_big = net.pos_vel_seq.clone()
+        again = net(x)
+        assert torch.equal(big, again)
+        small = net(x[100:103])
+        assert torch.equal(net.pos_vel_seq, pv_big[100:103])
+        assert torch.equal(small, big[100:103])
