@@ -11,6 +11,8 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <cstdint>
+
 namespace paig {
 
 constexpr int kConvThreads = 256;
@@ -20,7 +22,71 @@ constexpr int kCK = 8;                 // input channels staged per pass
 // conv3x3: each thread produces 4 horizontally adjacent pixels x CO_T output channels.
 // Block = FPB frames x TH rows x QX quads (<= 256 threads); blockIdx = (frame group, row strip, cout group).
 // ---------------------------------------------------------------------------------------------------------
-template <int CO_T>
+// Row-wise staging of NCHW rows into a zero-haloed shared tile (image column x sits at tile column x+1).
+// LOG_QX >= 0: S == 4 << LOG_QX and every pointer is 16-byte aligned, so a row is QX float4 loads and the
+// (frame, channel, row) of a thread's item advances incrementally -- no per-element div/mod.  LOG_QX < 0: generic.
+// rows: list index R -> (ff, ci, r) with r fastest; global row gy = y0 + r + yofs of channel cbase+ci, frame f0+ff,
+// stored at tile column col0.
+template <int LOG_QX>
+__device__ __forceinline__ void stage_rows(float* __restrict__ sDst, int plane, int cslots, int PITCH, int RT, int nfr,
+                                           int nc, const float* __restrict__ src, long src_bs,
+                                           const float* __restrict__ msk, long msk_bs, int cbase, int f0, int N, int y0,
+                                           int S, int tid, int nthr, int col0 = 1, int yofs = -1) {
+    if (LOG_QX >= 0) {
+        constexpr int QXc = LOG_QX >= 0 ? (1 << (LOG_QX >= 0 ? LOG_QX : 0)) : 1;
+        const int q = tid & (QXc - 1);
+        const int step = nthr >> (LOG_QX >= 0 ? LOG_QX : 0);
+        int R = tid >> (LOG_QX >= 0 ? LOG_QX : 0);
+        int r = R % RT, t = R / RT;
+        int ci = t % nc, ff = t / nc;
+        while (ff < nfr) {
+            const int gy = y0 + r + yofs, gf = f0 + ff;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gf < N && (unsigned)gy < (unsigned)S) {
+                const long off = ((long)(cbase + ci) * S + gy) * S + 4 * q;
+                v = *reinterpret_cast<const float4*>(src + (long)gf * src_bs + off);
+                if (msk) {
+                    const float4 m = *reinterpret_cast<const float4*>(msk + (long)gf * msk_bs + off);
+                    v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+                    v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+                }
+            }
+            float* d = sDst + (ff * cslots + ci) * plane + r * PITCH + col0 + 4 * q;
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            r += step;
+            while (r >= RT) {
+                r -= RT;
+                if (++ci == nc) { ci = 0; ++ff; }
+            }
+        }
+    } else {
+        const int rowlen = S;
+        const int total = nfr * nc * RT * rowlen;
+        for (int e = tid; e < total; e += nthr) {
+            const int col = e % rowlen, R = e / rowlen;
+            const int r = R % RT, t = R / RT, ci = t % nc, ff = t / nc;
+            const int gy = y0 + r + yofs, gf = f0 + ff;
+            float v = 0.f;
+            if (gf < N && (unsigned)gy < (unsigned)S) {
+                const long off = ((long)(cbase + ci) * S + gy) * S + col;
+                v = src[(long)gf * src_bs + off];
+                if (msk && !(msk[(long)gf * msk_bs + off] > 0.f)) v = 0.f;
+            }
+            sDst[(ff * cslots + ci) * plane + r * PITCH + col0 + col] = v;
+        }
+    }
+}
+
+// zero the halo columns (tile column 0 and columns S+1 .. PITCH-1) of every staged row once per CTA
+__device__ __forceinline__ void zero_halo_cols(float* sDst, int rows_total, int PITCH, int S, int tid, int nthr) {
+    const int hc = PITCH - S;                   // 1 left + (PITCH - S - 1) right
+    for (int e = tid; e < rows_total * hc; e += nthr) {
+        const int row = e / hc, k = e % hc;
+        sDst[row * PITCH + (k == 0 ? 0 : S + k)] = 0.f;
+    }
+}
+
+template <int CO_T, int LOG_QX>
 __global__ void __launch_bounds__(kConvThreads) conv3x3_kernel(ConvArgs a) {
     PAIG_DYN_SMEM(float, smem);
     const int S = a.S, QX = a.QX, TH = a.TH, FPB = a.FPB;
@@ -40,21 +106,13 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_kernel(ConvArgs a) {
 #pragma unroll
         for (int p = 0; p < 4; ++p) acc[c][p] = 0.f;
 
+    zero_halo_cols(sIn, FPB * kCK * (TH + 2), PITCH, S, tid, nthr);     // plane == (TH+2)*PITCH: rows are contiguous
+
     for (int c0 = 0; c0 < a.Cin; c0 += kCK) {
         const int nc = min(kCK, a.Cin - c0);
         // ---- stage the input tile (zero halo), optionally masked by the producer's ReLU ----
-        const int tile_elems = FPB * nc * plane;
-        for (int e = tid; e < tile_elems; e += nthr) {
-            const int col = e % PITCH, r = (e / PITCH) % (TH + 2), ci = (e / plane) % nc, ff = e / (plane * nc);
-            const int gy = y0 + r - 1, gx = col - 1, gf = f0 + ff;
-            float v = 0.f;
-            if (gf < a.N && (unsigned)gy < (unsigned)S && (unsigned)gx < (unsigned)S) {
-                const long off = ((long)(c0 + ci) * S + gy) * S + gx;
-                v = a.in[(long)gf * a.in_bs + off];
-                if (a.mask && !(a.mask[(long)gf * a.mask_bs + off] > 0.f)) v = 0.f;
-            }
-            sIn[(ff * kCK + ci) * plane + r * PITCH + col] = v;
-        }
+        stage_rows<LOG_QX>(sIn, plane, kCK, PITCH, TH + 2, FPB, nc, a.in, a.in_bs, a.mask, a.mask_bs, c0, f0, a.N, y0, S,
+                           tid, nthr);
         // ---- stage the weights of this (cin chunk, cout group): sW[ci][tap][co] ----
         for (int e = tid; e < nc * 9 * CO_T; e += nthr) {
             const int co = e % CO_T, tap = (e / CO_T) % 9, ci = e / (9 * CO_T);
@@ -147,8 +205,30 @@ int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
     const int CO_T = wide ? 16 : 8;
     const size_t smem = ((size_t)a.FPB * kCK * (a.TH + 2) * PITCH + (size_t)kCK * 9 * CO_T) * sizeof(float);
     dim3 grid(cdiv(a.N, a.FPB), strips, cdiv(a.Cout, CO_T));
-    if (wide) launch(conv3x3_kernel<16>, grid, dim3(threads), smem, st, a);
-    else launch(conv3x3_kernel<8>, grid, dim3(threads), smem, st, a);
+    // vector staging needs S = 4 * 2^k and 16-byte aligned rows
+    int lq = -1;
+    const bool aligned = ((uintptr_t)a.in % 16 == 0) && (a.in_bs % 4 == 0) &&
+                         (!a.mask || (((uintptr_t)a.mask % 16 == 0) && (a.mask_bs % 4 == 0)));
+    if (aligned && a.S == 4 * a.QX) {
+        for (int k = 0; k <= 4; ++k)
+            if (a.QX == (1 << k)) lq = k;
+    }
+    dim3 blk(threads);
+#define PAIG_CONV_CASE(LQ)                                                                  \
+    case LQ:                                                                                \
+        if (wide) launch(conv3x3_kernel<16, LQ>, grid, blk, smem, st, a);                   \
+        else launch(conv3x3_kernel<8, LQ>, grid, blk, smem, st, a);                         \
+        break;
+    switch (lq) {
+        PAIG_CONV_CASE(1)
+        PAIG_CONV_CASE(2)
+        PAIG_CONV_CASE(3)
+        PAIG_CONV_CASE(4)
+        default:
+            if (wide) launch(conv3x3_kernel<16, -1>, grid, blk, smem, st, a);
+            else launch(conv3x3_kernel<8, -1>, grid, blk, smem, st, a);
+    }
+#undef PAIG_CONV_CASE
     return check_launch("conv3x3");
 }
 
@@ -160,6 +240,7 @@ int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kWgTH = 8;                  // rows per staged strip
 
+template <int LOG_QX>
 __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a) {
     PAIG_DYN_SMEM(float, smem);
     const int S = a.S, QX = (S + 3) / 4;
@@ -187,34 +268,19 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
 #pragma unroll
         for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
     }
+    // halo columns / plane padding are never written by the row staging: clear the tile once
+    for (int e = tid; e < a.Cin * in_plane + a.Cout * g_plane; e += kConvThreads) smem[e] = 0.f;
+    __syncthreads();
     const int strips = (S + kWgTH - 1) / kWgTH;
     const int items = a.N * strips;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int f = item / strips, y0 = (item % strips) * kWgTH;
         const int rows = min(kWgTH, S - y0);
-        // ---- stage input strip (halo rows/cols zero) ----
-        for (int e = tid; e < a.Cin * (kWgTH + 2) * PITCH; e += kConvThreads) {
-            const int col = e % PITCH, r = (e / PITCH) % (kWgTH + 2), c = e / (PITCH * (kWgTH + 2));
-            const int gy = y0 + r - 1, gx = col - 1;
-            float v = 0.f;
-            if (r < rows + 2 && (unsigned)gy < (unsigned)S && (unsigned)gx < (unsigned)S) {
-                const long off = ((long)c * S + gy) * S + gx;
-                v = a.in[(long)f * a.in_bs + off];
-                if (a.in_mask && !(a.in_mask[(long)f * a.in_mask_bs + off] > 0.f)) v = 0.f;
-            }
-            sIn[c * in_plane + r * PITCH + col] = v;
-        }
-        // ---- stage masked output gradient strip ----
-        for (int e = tid; e < a.Cout * kWgTH * GP; e += kConvThreads) {
-            const int col = e % GP, r = (e / GP) % kWgTH, c = e / (GP * kWgTH);
-            float v = 0.f;
-            if (r < rows && col < S) {
-                const long off = ((long)c * S + (y0 + r)) * S + col;
-                v = a.g[(long)f * a.g_bs + off];
-                if (a.act && !(a.act[(long)f * a.act_bs + off] > 0.f)) v = 0.f;
-            }
-            sG[c * g_plane + r * GP + col] = v;
-        }
+        // ---- stage input strip (zero halo) and the masked output-gradient strip ----
+        stage_rows<LOG_QX>(sIn, in_plane, 0, PITCH, kWgTH + 2, 1, a.Cin, a.in, a.in_bs, a.in_mask, a.in_mask_bs, 0, f, a.N,
+                           y0, S, tid, kConvThreads);
+        stage_rows<LOG_QX>(sG, g_plane, 0, GP, kWgTH, 1, a.Cout, a.g, a.g_bs, a.act, a.act_bs, 0, f, a.N, y0, S, tid,
+                           kConvThreads, 0, 0);
         __syncthreads();
         if (owner) {
             const int nq = rows * QX;
@@ -324,7 +390,21 @@ int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t s
     const int strips = cdiv(a.S, kWgTH);
     int ctas = a.N * strips;
     if (ctas > kWgradMaxCtas) ctas = kWgradMaxCtas;
-    launch(conv3x3_wgrad_kernel, dim3(ctas, gsets), dim3(kConvThreads), smem, st, a);
+    int lq = -1;
+    const bool aligned = ((uintptr_t)a.in % 16 == 0) && (a.in_bs % 4 == 0) && ((uintptr_t)a.g % 16 == 0) &&
+                         (a.g_bs % 4 == 0) && (!a.act || (((uintptr_t)a.act % 16 == 0) && (a.act_bs % 4 == 0))) &&
+                         !a.in_mask;
+    if (aligned && a.S == 4 * QX)
+        for (int k = 0; k <= 4; ++k)
+            if (QX == (1 << k)) lq = k;
+    const dim3 wg_grid(ctas, gsets), wg_blk(kConvThreads);
+    switch (lq) {
+        case 1: launch(conv3x3_wgrad_kernel<1>, wg_grid, wg_blk, smem, st, a); break;
+        case 2: launch(conv3x3_wgrad_kernel<2>, wg_grid, wg_blk, smem, st, a); break;
+        case 3: launch(conv3x3_wgrad_kernel<3>, wg_grid, wg_blk, smem, st, a); break;
+        case 4: launch(conv3x3_wgrad_kernel<4>, wg_grid, wg_blk, smem, st, a); break;
+        default: launch(conv3x3_wgrad_kernel<-1>, wg_grid, wg_blk, smem, st, a);
+    }
     int rc = check_launch("conv3x3_wgrad");
     if (rc) return rc;
     const int nW = a.Cout * a.Cin * 9;
