@@ -165,7 +165,13 @@ Layout make_layout(const paig_task* t, int B) {
     L.scales = take(d.e + d.steps);
     L.losses = take(8);
     L.dphys = take(8);
+    {   // room for the split-K partials of encoder.l1 forward ([splits][nN][200]) and weight gradient ([splits][200][K])
+        const size_t fwd = (size_t)cdiv(L.K, 512) * nN * kHidden, wg = 4 * (size_t)kHidden * L.K;
+        const size_t sk = fwd > wg ? fwd : wg;
+        max_w = sk > max_w ? sk : max_w;
+    }
     L.partials = take(max_w);
+    L.partials_floats = max_w;
     L.frames = take(N * d.CHW);
     L.x_stage = take((size_t)B * d.T * d.CHW);
     L.total = off;
@@ -445,7 +451,9 @@ int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, c
         cudaMemcpyAsync(enc_masks_out, masks, (size_t)L.N * (d.n + 1) * d.HW * sizeof(float), cudaMemcpyDeviceToDevice,
                         st);
     const int M = d.n * L.N;
-    if ((rc = linear_forward(ws + L.A, p->enc_l1.w, p->enc_l1.b, ws + L.H1, M, L.K, kHidden, EPI_RELU, st))) return rc;
+    if ((rc = linear_forward(ws + L.A, p->enc_l1.w, p->enc_l1.b, ws + L.H1, M, L.K, kHidden, EPI_RELU, st, ws + L.partials,
+                             L.partials_floats, "sgemm_l1_fwd")))
+        return rc;
     if ((rc = linear_forward(ws + L.H1, p->enc_l2.w, p->enc_l2.b, ws + L.H2, M, kHidden, kHidden, EPI_RELU, st)))
         return rc;
     if ((rc = linear_forward(ws + L.H2, p->enc_l3.w, p->enc_l3.b, ws + L.O3, M, kHidden, 2, EPI_NONE, st))) return rc;
@@ -465,15 +473,23 @@ int encoder_backward(const paig_task* t, const paig_params* p, const paig_params
            (float)d.H * 0.5f, d_enc_pos, ws + L.dO3);
     if ((rc = check_launch("pos_head_bwd"))) return rc;
     // l3
-    if ((rc = linear_wgrad(ws + L.dO3, ws + L.H2, g->enc_l3.w, g->enc_l3.b, M, kHidden, 2, st))) return rc;
+    if ((rc = linear_wgrad(ws + L.dO3, ws + L.H2, g->enc_l3.w, g->enc_l3.b, M, kHidden, 2, st, ws + L.partials,
+                           L.partials_floats)))
+        return rc;
     if ((rc = linear_dgrad(ws + L.dO3, p->enc_l3.w, ws + L.dH2, M, kHidden, 2, EPI_MASK_RELU, ws + L.H2, st))) return rc;
     // l2
-    if ((rc = linear_wgrad(ws + L.dH2, ws + L.H1, g->enc_l2.w, g->enc_l2.b, M, kHidden, kHidden, st))) return rc;
+    if ((rc = linear_wgrad(ws + L.dH2, ws + L.H1, g->enc_l2.w, g->enc_l2.b, M, kHidden, kHidden, st, ws + L.partials,
+                           L.partials_floats)))
+        return rc;
     if ((rc = linear_dgrad(ws + L.dH2, p->enc_l2.w, ws + L.dH1, M, kHidden, kHidden, EPI_MASK_RELU, ws + L.H1, st)))
         return rc;
     // l1
-    if ((rc = linear_wgrad(ws + L.dH1, ws + L.A, g->enc_l1.w, g->enc_l1.b, M, L.K, kHidden, st))) return rc;
-    if ((rc = linear_dgrad(ws + L.dH1, p->enc_l1.w, ws + L.dA, M, L.K, kHidden, EPI_NONE, nullptr, st))) return rc;
+    if ((rc = linear_wgrad(ws + L.dH1, ws + L.A, g->enc_l1.w, g->enc_l1.b, M, L.K, kHidden, st, ws + L.partials,
+                           L.partials_floats, "sgemm_l1_wgrad")))
+        return rc;
+    if ((rc = linear_dgrad(ws + L.dH1, p->enc_l1.w, ws + L.dA, M, L.K, kHidden, EPI_NONE, nullptr, st, nullptr, 0,
+                           "sgemm_l1_dgrad")))
+        return rc;
     switch (d.n) {
         case 1: rc = masks_bwd<1>(L, t->deep_unet, ws, x, seq_stride, fps, st); break;
         case 2: rc = masks_bwd<2>(L, t->deep_unet, ws, x, seq_stride, fps, st); break;
@@ -582,17 +598,17 @@ int velocity_backward(const paig_task* t, const paig_params* p, const paig_param
     if (!has_vel) return 0;
     const int M = d.n * L.B, cols = t->alt_vel ? 2 * (d.in - 1) : 2 * d.in;
     if (t->alt_vel) {
-        if ((rc = linear_wgrad(ws + L.dvout, ws + L.vin, g->vel[0].w, g->vel[0].b, M, cols, 2, st))) return rc;
+        if ((rc = linear_wgrad(ws + L.dvout, ws + L.vin, g->vel[0].w, g->vel[0].b, M, cols, 2, st, ws + L.partials, L.partials_floats))) return rc;
         if ((rc = linear_dgrad(ws + L.dvout, p->vel[0].w, ws + L.dvin, M, cols, 2, EPI_NONE, nullptr, st))) return rc;
     } else {
-        if ((rc = linear_wgrad(ws + L.dvout, ws + L.v2, g->vel[2].w, g->vel[2].b, M, kVelHidden, 2, st))) return rc;
+        if ((rc = linear_wgrad(ws + L.dvout, ws + L.v2, g->vel[2].w, g->vel[2].b, M, kVelHidden, 2, st, ws + L.partials, L.partials_floats))) return rc;
         if ((rc = linear_dgrad(ws + L.dvout, p->vel[2].w, ws + L.dv2, M, kVelHidden, 2, EPI_MASK_TANH, ws + L.v2, st)))
             return rc;
-        if ((rc = linear_wgrad(ws + L.dv2, ws + L.v1, g->vel[1].w, g->vel[1].b, M, kVelHidden, kVelHidden, st))) return rc;
+        if ((rc = linear_wgrad(ws + L.dv2, ws + L.v1, g->vel[1].w, g->vel[1].b, M, kVelHidden, kVelHidden, st, ws + L.partials, L.partials_floats))) return rc;
         if ((rc = linear_dgrad(ws + L.dv2, p->vel[1].w, ws + L.dv1, M, kVelHidden, kVelHidden, EPI_MASK_TANH, ws + L.v1,
                                st)))
             return rc;
-        if ((rc = linear_wgrad(ws + L.dv1, ws + L.vin, g->vel[0].w, g->vel[0].b, M, cols, kVelHidden, st))) return rc;
+        if ((rc = linear_wgrad(ws + L.dv1, ws + L.vin, g->vel[0].w, g->vel[0].b, M, cols, kVelHidden, st, ws + L.partials, L.partials_floats))) return rc;
         if ((rc = linear_dgrad(ws + L.dv1, p->vel[0].w, ws + L.dvin, M, cols, kVelHidden, EPI_NONE, nullptr, st)))
             return rc;
     }

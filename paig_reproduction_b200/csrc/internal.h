@@ -77,6 +77,7 @@ int upsample2(const float* in, long in_bs, float* out, long out_bs, int C, int S
 int upsample2_backward(const float* dout, long dout_bs, float* din, long din_bs, int C, int Si, int N, cudaStream_t st);
 
 // gemm.cu
+enum { SPLIT_NONE = 0, SPLIT_FIXED = 1, SPLIT_AUTO = 2 };
 enum { EPI_NONE = 0, EPI_RELU = 1, EPI_TANH = 2, EPI_MASK_RELU = 3, EPI_MASK_TANH = 4 };
 struct GemmArgs {
     const float* A = nullptr; long sam = 0, sak = 0;     // A(m,k) = A[m*sam + k*sak]
@@ -87,13 +88,18 @@ struct GemmArgs {
     int epi = EPI_NONE;
     const float* aux = nullptr; long ldaux = 0;          // activation the MASK_* epilogues differentiate
     int accumulate = 0;                                  // C += result
+    float* splitk_ws = nullptr; size_t splitk_floats = 0; // optional scratch for split-K partials ([splits][M][N])
+    int split_mode = 0;                                  // SPLIT_*
+    const char* tag = nullptr;                           // name in the per-launch profile (default "sgemm")
+    int a_vec = 0, b_vec = 0, kper = 0;                  // filled by gemm(): 16-byte global loads legal; K per split
 };
 int gemm(const GemmArgs& g, cudaStream_t st);
 int colsum(const float* X, int M, int N, int ld, float* out, cudaStream_t st);
 int linear_forward(const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int epi,
-                   cudaStream_t st);
+                   cudaStream_t st, float* splitk_ws = nullptr, size_t splitk_floats = 0, const char* tag = nullptr);
 int linear_dgrad(const float* dY, const float* W, float* dX, int M, int K, int N, int epi, const float* aux,
-                 cudaStream_t st);
-int linear_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int K, int N, cudaStream_t st);
+                 cudaStream_t st, float* splitk_ws = nullptr, size_t splitk_floats = 0, const char* tag = nullptr);
+int linear_wgrad(const float* dY, const float* X, float* dW, float* db, int M, int K, int N, cudaStream_t st,
+                 float* splitk_ws = nullptr, size_t splitk_floats = 0, const char* tag = nullptr);
 
 }  // namespace paig

@@ -45,7 +45,8 @@ struct Layout {
     size_t seq, d_seq, d_state0;
     size_t raw, consts, hidden, d_consts, dec_partials, tmpl_scratch;
     size_t sse, scales, losses, dphys;
-    size_t partials;             // conv wgrad / head partial sums
+    size_t partials;             // conv wgrad / head partial sums; split-K partials of the MLP GEMMs
+    size_t partials_floats;
     size_t frames;               // gathered encoder frames [N,3,H,H] (when they are a prefix of each sequence)
     size_t x_stage;              // device copy of the input for the *_host entry point
     size_t total;
