@@ -8,6 +8,8 @@
 #include "internal.h"
 #include "layout.h"
 
+#include <cstdlib>
+
 namespace paig {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -172,6 +174,7 @@ Layout make_layout(const paig_task* t, int B) {
     }
     L.partials = take(max_w);
     L.partials_floats = max_w;
+    L.wpack = take(unet_wpack_floats(L.unet, t));
     L.frames = take(N * d.CHW);
     L.x_stage = take((size_t)B * d.T * d.CHW);
     L.total = off;
@@ -438,7 +441,11 @@ int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, c
         if (rc0) return rc0;
         frames = dst;
     }
-    int rc = unet_forward(t, p, L, ws, frames, st);
+    // whole UNet in one persistent kernel when a frame's activations fit in shared memory (ShallowUNet); the
+    // per-layer interpreter otherwise (64x64 UNet) or when PAIG_UNET_LAYERWISE=1 (A/B measurements)
+    static const bool layerwise = getenv("PAIG_UNET_LAYERWISE") != nullptr;
+    int rc = layerwise ? -1 : unet_fused_forward(t, p, L, x, seq_stride, fps, ws, st);
+    if (rc < 0) rc = unet_forward(t, p, L, ws, frames, st);
     if (rc) return rc;
     float* masks = ws + L.masks;
     switch (d.n) {

@@ -47,12 +47,18 @@ struct Layout {
     size_t sse, scales, losses, dphys;
     size_t partials;             // conv wgrad / head partial sums; split-K partials of the MLP GEMMs
     size_t partials_floats;
+    size_t wpack;                // UNet weights re-packed [ci][tap][co]|bias for the fused forward kernel
     size_t frames;               // gathered encoder frames [N,3,H,H] (when they are a prefix of each sequence)
     size_t x_stage;              // device copy of the input for the *_host entry point
     size_t total;
 };
 
 Layout make_layout(const paig_task* t, int B);
+
+// unet_fused.cu -- whole-UNet forward in one persistent kernel; returns -1 when the network does not fit on chip
+size_t unet_wpack_floats(const UNetDesc& u, const paig_task* t);
+int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride, int fps,
+                       float* ws, cudaStream_t st);
 
 // encoder.cu
 int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride,
