@@ -344,21 +344,40 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
     }
 }
 
-// out[i] = sum_p partials[p*stride + i]   (fixed order => deterministic); two destinations (weights, bias).
+// out[i] = sum_p partials[p*stride + i]; two destinations (weights, bias).  A block reduces 32 outputs: its 8 warps
+// each sum a strided subset of the partials (coalesced 128-byte rows), then fold through shared memory in a fixed
+// order, so the result is deterministic and the long dimension is read in parallel.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int nparts, int stride,
                                                               int n0, float* __restrict__ out0, int n1,
                                                               float* __restrict__ out1) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n0 + n1) return;
-    float s = 0.f;
-    for (int p = 0; p < nparts; ++p) s += partials[(size_t)p * stride + i];
-    if (i < n0) out0[i] = s;
-    else if (out1) out1[i - n0] = s;
+    __shared__ float part[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < n0 + n1) {
+        int p = w;
+        for (; p + 24 < nparts; p += 32) {          // four independent loads in flight
+            s0 += partials[(size_t)p * stride + i];
+            s1 += partials[(size_t)(p + 8) * stride + i];
+            s2 += partials[(size_t)(p + 16) * stride + i];
+            s3 += partials[(size_t)(p + 24) * stride + i];
+        }
+        for (; p < nparts; p += 8) s0 += partials[(size_t)p * stride + i];
+    }
+    part[w][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w == 0 && i < n0 + n1) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += part[k][lane];
+        if (i < n0) out0[i] = s;
+        else if (out1) out1[i - n0] = s;
+    }
 }
 
 int reduce_partials(const float* partials, int nparts, int stride, int n0, float* out0, int n1, float* out1,
                     cudaStream_t st) {
-    launch(reduce_partials_kernel, dim3(cdiv(n0 + n1, 256)), dim3(256), 0, st, partials, nparts, stride, n0, out0, n1,
+    launch(reduce_partials_kernel, dim3(cdiv(n0 + n1, 32)), dim3(256), 0, st, partials, nparts, stride, n0, out0, n1,
            out1);
     return check_launch("reduce_partials");
 }
@@ -604,12 +623,14 @@ __global__ void __launch_bounds__(256) upsample2_kernel(const float* __restrict_
     out[f * out_bs + ((long)c * So + y) * So + x] = wya * top + wyb * bot;
 }
 
-// adjoint: din[i,j] = sum over the (<= 4x4) outputs that read in[i,j] of weight * dout   (gather, written)
-__device__ __forceinline__ float up_weight(int o, int i, int Si) {
-    int i0, i1;
-    float w0, w1;
-    up_taps(o, Si, i0, i1, w0, w1);
-    return (i0 == i ? w0 : 0.f) + (i1 == i ? w1 : 0.f);
+// adjoint (gather, written): input i feeds outputs 2i-1 (.25), 2i (.75), 2i+1 (.75), 2i+2 (.25); at the borders the
+// clamped taps fold back: output 0 reads input 0 with .25 + .75 = 1, output So-1 reads input Si-1 with 1.
+__device__ __forceinline__ void up_adj(int i, int Si, int& o0, float (&w)[4]) {
+    o0 = 2 * i - 1;
+    w[0] = i > 0 ? 0.25f : 0.f;
+    w[1] = i > 0 ? 0.75f : 1.f;
+    w[2] = i < Si - 1 ? 0.75f : 1.f;
+    w[3] = i < Si - 1 ? 0.25f : 0.f;
 }
 
 __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restrict__ dout, long dout_bs,
@@ -621,13 +642,21 @@ __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restr
     const int j = (int)(idx % Si), i = (int)((idx / Si) % Si), c = (int)((idx / ((long)Si * Si)) % C);
     const long f = idx / ((long)Si * Si * C);
     const float* g = dout + f * dout_bs + (long)c * So * So;
+    int oy0, ox0;
+    float wy[4], wx[4];
+    up_adj(i, Si, oy0, wy);
+    up_adj(j, Si, ox0, wx);
     float s = 0.f;
-    for (int oy = max(2 * i - 1, 0); oy <= min(2 * i + 2, So - 1); ++oy) {
-        const float wy = up_weight(oy, i, Si);
-        if (wy == 0.f) continue;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int oy = oy0 + a;
+        if (wy[a] == 0.f) continue;
+        const float* row = g + oy * So + ox0;
         float r = 0.f;
-        for (int ox = max(2 * j - 1, 0); ox <= min(2 * j + 2, So - 1); ++ox) r += up_weight(ox, j, Si) * g[oy * So + ox];
-        s += wy * r;
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+            if (wx[b] != 0.f) r += wx[b] * row[b];
+        s += wy[a] * r;
     }
     din[f * din_bs + ((long)c * Si + i) * Si + j] = s;
 }

@@ -28,7 +28,7 @@ namespace paig {
 
 constexpr int kFusedThreads = 512;
 constexpr int kFusedMaxOps = 24;
-constexpr size_t kFusedSmemLimit = 227 * 1024 - 64;
+constexpr size_t kFusedSmemLimit = 227 * 1024 - 4096;   // dynamic part; the op table and barriers are static
 
 enum { F_CONV = 0, F_POOL = 1, F_HEAD = 2 };
 
@@ -49,6 +49,7 @@ struct FusedPlan {
     int x_off;
     const float* x;
     const float* wpack;
+    long long* timing;             // debug (PAIG_DEBUG): per-CTA cycle stamps after every op of the CTA's first frames
     FusedOp ops[kFusedMaxOps];
 };
 
@@ -96,12 +97,18 @@ __device__ __forceinline__ void bulk_wait(unsigned long long* bar, unsigned phas
 #endif
 }
 
-// zero the halo (row 0, row S+1, column 0, columns S+1..P-1) of C consecutive planes
+#ifdef PAIG_EMU
+#define PAIG_STAMP(tm, i)
+#else
+#define PAIG_STAMP(tm, i) do { if (tm) (tm)[i] = clock64(); } while (0)
+#endif
+
+// zero the halo (row 0, row S+1, column 0, columns S+1..P-1) of C consecutive planes: a thread owns one halo cell
+// (<= 2P + S(P-S) = 224 cells for S <= 36) and walks the planes, so the index arithmetic is done once
 __device__ __forceinline__ void zero_halo_planes(float* base, int C, const Geo g, int tid, int nthr) {
     const int side = g.P - g.S;                        // halo cells per interior row
     const int per = 2 * g.P + g.S * side;
-    for (int e = tid; e < C * per; e += nthr) {
-        const int c = e / per, k = e % per;
+    for (int k = tid; k < per; k += nthr) {
         int row, col;
         if (k < 2 * g.P) {
             row = k < g.P ? 0 : g.S + 1;
@@ -111,33 +118,42 @@ __device__ __forceinline__ void zero_halo_planes(float* base, int C, const Geo g
             row = 1 + k2 / side;
             col = j == 0 ? 0 : g.S + j;
         }
-        base[c * g.plane + row * g.P + col] = 0.f;
+        float* p = base + row * g.P + col;
+        for (int c = 0; c < C; ++c) p[c * g.plane] = 0.f;
     }
 }
 
 // acc[c][p] += sum_{ci < nci} sum_taps w[ci][tap][c] * in[ci][y + ky - 1][4 qx + p + kx - 1]
-template <int CO>
+// COUT is a template parameter so that every weight load is [pointer + immediate]; the three row pointers advance
+// by one plane per input channel.
+template <int CO, int COUT>
 __device__ __forceinline__ void conv_accumulate(float (&acc)[CO][4], const float* __restrict__ planes, int nci,
-                                                const Geo g, const float* __restrict__ w, int Cout, int y, int qx) {
-    const float* row0 = planes + y * g.P + 4 * qx;
+                                                const Geo g, const float* __restrict__ w, int y, int qx) {
+    const float* r0 = planes + y * g.P + 4 * qx;
+    const float* r1 = r0 + g.P;
+    const float* r2 = r1 + g.P;
+    const int plane = g.plane;
+#pragma unroll 2
     for (int ci = 0; ci < nci; ++ci) {
-        const float* row = row0 + ci * g.plane;
         float v[3][6];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            const float4 p4 = *reinterpret_cast<const float4*>(row + r * g.P);
-            const float2 p2 = *reinterpret_cast<const float2*>(row + r * g.P + 4);
-            v[r][0] = p4.x; v[r][1] = p4.y; v[r][2] = p4.z; v[r][3] = p4.w; v[r][4] = p2.x; v[r][5] = p2.y;
+        {
+            const float4 a4 = *reinterpret_cast<const float4*>(r0);
+            const float2 a2 = *reinterpret_cast<const float2*>(r0 + 4);
+            const float4 b4 = *reinterpret_cast<const float4*>(r1);
+            const float2 b2 = *reinterpret_cast<const float2*>(r1 + 4);
+            const float4 c4 = *reinterpret_cast<const float4*>(r2);
+            const float2 c2 = *reinterpret_cast<const float2*>(r2 + 4);
+            v[0][0] = a4.x; v[0][1] = a4.y; v[0][2] = a4.z; v[0][3] = a4.w; v[0][4] = a2.x; v[0][5] = a2.y;
+            v[1][0] = b4.x; v[1][1] = b4.y; v[1][2] = b4.z; v[1][3] = b4.w; v[1][4] = b2.x; v[1][5] = b2.y;
+            v[2][0] = c4.x; v[2][1] = c4.y; v[2][2] = c4.z; v[2][3] = c4.w; v[2][4] = c2.x; v[2][5] = c2.y;
         }
-        const float* wp = w + ci * 9 * Cout;
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
-                const float* wt = wp + (ky * 3 + kx) * Cout;
 #pragma unroll
                 for (int c4 = 0; c4 < CO; c4 += 4) {
-                    const float4 w4 = *reinterpret_cast<const float4*>(wt + c4);
+                    const float4 w4 = *reinterpret_cast<const float4*>(w + (ky * 3 + kx) * COUT + c4);
                     const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                     for (int c = 0; c < 4; ++c)
@@ -145,6 +161,8 @@ __device__ __forceinline__ void conv_accumulate(float (&acc)[CO][4], const float
                         for (int p = 0; p < 4; ++p) acc[c4 + c][p] += wv[c] * v[ky][kx + p];
                 }
             }
+        r0 += plane; r1 += plane; r2 += plane;
+        w += 9 * COUT;
     }
 }
 
@@ -188,25 +206,90 @@ __device__ __forceinline__ void conv_epilogue(const float (&acc)[CO][4], const F
     }
 }
 
-template <int CO>
-__device__ __forceinline__ void run_conv(const FusedOp& op, float* sm, int f, int tid) {
+// 2x bilinear upsample (align_corners=False) of channels [c0, c0+nch) of a half-resolution buffer into `chunk`
+// (and to global memory for the backward pass).  A thread owns one 4-pixel output quad position and strides over
+// the channels; per channel it reads 2 source rows x 4 source columns (two 8-byte loads each) and blends W first,
+// then H -- the arithmetic of conv.cu's upsample2_kernel.  No per-element index arithmetic.
+__device__ __forceinline__ void upsample_chunk(const float* __restrict__ src, const Geo gl, float* __restrict__ chunk,
+                                               const Geo g, int nch, float* __restrict__ gdst, int tid) {
+    const int S = g.S, Si = gl.S;
+    const int nq = S * g.nqx;                       // output quads per channel
+    if (tid >= (kFusedThreads / nq) * nq && nq <= kFusedThreads) return;
+    const int q = tid % nq, sub = tid / nq, nsub = kFusedThreads / nq > 0 ? kFusedThreads / nq : 1;
+    if (tid >= nq && nq > kFusedThreads) return;    // (never: nq <= 324)
+    const int yy = q / g.nqx, qx = q % g.nqx, x0 = 4 * qx;
+    // rows: out row yy reads source rows ya, yb with weights wya, wyb
+    int ya, yb;
+    float wya, wyb;
+    up_taps_f(yy, Si, ya, yb, wya, wyb);
+    // columns: outputs x0..x0+3 read source columns k-1..k+2 with k = x0/2 (even x: .25 in[k-1] + .75 in[k]; odd x:
+    // .75 in[k] + .25 in[k+1]); clamped at the borders
+    const int k = x0 >> 1;
+    const bool left = k == 0;                        // column k-1 is outside: clamp to column 0
+    const int kmax = Si - 1;
+    const float* pa = src + (ya + 1) * gl.P + k;     // tile column of source column k-1 is k
+    const float* pb = src + (yb + 1) * gl.P + k;
+    float* cd = chunk + (yy + 1) * g.P + x0 + 1;
+    const bool vec = (S & 3) == 0;
+    for (int c = sub; c < nch; c += nsub) {
+        const float2 a01 = *reinterpret_cast<const float2*>(pa + c * gl.plane);
+        const float2 a23 = *reinterpret_cast<const float2*>(pa + c * gl.plane + 2);
+        const float2 b01 = *reinterpret_cast<const float2*>(pb + c * gl.plane);
+        const float2 b23 = *reinterpret_cast<const float2*>(pb + c * gl.plane + 2);
+        float a[4] = {a01.x, a01.y, a23.x, a23.y}, b[4] = {b01.x, b01.y, b23.x, b23.y};
+        if (left) { a[0] = a[1]; b[0] = b[1]; }
+        if (k + 1 > kmax) { a[2] = a[1]; b[2] = b[1]; }           // (only when the quad is partly outside the image)
+        if (k + 2 > kmax) { a[3] = k + 1 > kmax ? a[1] : a[2]; b[3] = k + 1 > kmax ? b[1] : b[2]; }
+        // W pass: x0 (even): .25 s[k-1] + .75 s[k]; x0+1: .75 s[k] + .25 s[k+1]; x0+2: .25 s[k] + .75 s[k+1]; x0+3: .75 s[k+1] + .25 s[k+2]
+        float top[4], bot[4], o[4];
+        top[0] = 0.25f * a[0] + 0.75f * a[1]; bot[0] = 0.25f * b[0] + 0.75f * b[1];
+        top[1] = 0.75f * a[1] + 0.25f * a[2]; bot[1] = 0.75f * b[1] + 0.25f * b[2];
+        top[2] = 0.25f * a[1] + 0.75f * a[2]; bot[2] = 0.25f * b[1] + 0.75f * b[2];
+        top[3] = 0.75f * a[2] + 0.25f * a[3]; bot[3] = 0.75f * b[2] + 0.25f * b[3];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) o[p] = wya * top[p] + wyb * bot[p];
+        float* d = cd + c * g.plane;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+            if (vec || x0 + p < S) d[p] = o[p];
+        if (gdst) {
+            float* gd = gdst + ((long)c * S + yy) * S + x0;
+            if (vec) *reinterpret_cast<float4*>(gd) = make_float4(o[0], o[1], o[2], o[3]);
+            else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (x0 + p < S) gd[p] = o[p];
+            }
+        }
+    }
+}
+
+template <int CO, int COUT>
+__device__ __forceinline__ void run_conv(const FusedOp& op, float* sm, int f, int tid, long long* tm) {
     const Geo g = geo_of(op.S);
-    const int nq = op.S * g.nqx, ncg = op.Cout / CO, nitems = nq * ncg;
+    const int nq = op.S * g.nqx, nitems = nq * (COUT / CO);
     const float* w = sm + op.wsm;
-    const float* bias = w + (op.Cin0 + op.Cin1) * 9 * op.Cout;
-    if (op.out >= 0) zero_halo_planes(sm + op.out, op.Cout, g, tid, kFusedThreads);
+    const float* bias = w + (op.Cin0 + op.Cin1) * 9 * COUT;
+    if (op.out >= 0) zero_halo_planes(sm + op.out, COUT, g, tid, kFusedThreads);
+    PAIG_STAMP(tm, 1);
     if (!op.up) {
+        const bool pow2 = (nq & (nq - 1)) == 0 && (g.nqx & (g.nqx - 1)) == 0;
+        const int lq = 31 - __clz(nq), lx = 31 - __clz(g.nqx);
         for (int item = tid; item < nitems; item += kFusedThreads) {
-            const int cg = item / nq, q = item % nq, y = q / g.nqx, qx = q % g.nqx;
+            int cg, q, y, qx;
+            if (pow2) { cg = item >> lq; q = item & (nq - 1); y = q >> lx; qx = q & (g.nqx - 1); }
+            else { cg = item / nq; q = item % nq; y = q / g.nqx; qx = q % g.nqx; }
             float acc[CO][4];
 #pragma unroll
             for (int c = 0; c < CO; ++c)
 #pragma unroll
                 for (int p = 0; p < 4; ++p) acc[c][p] = 0.f;
-            conv_accumulate<CO>(acc, sm + op.in0, op.Cin0, g, w + cg * CO, op.Cout, y, qx);
-            if (op.Cin1) conv_accumulate<CO>(acc, sm + op.in1, op.Cin1, g, w + op.Cin0 * 9 * op.Cout + cg * CO, op.Cout, y, qx);
+            conv_accumulate<CO, COUT>(acc, sm + op.in0, op.Cin0, g, w + cg * CO, y, qx);
+            if (op.Cin1) conv_accumulate<CO, COUT>(acc, sm + op.in1, op.Cin1, g, w + op.Cin0 * 9 * COUT + cg * CO, y, qx);
+            PAIG_STAMP(tm, 2);
             conv_epilogue<CO>(acc, op, g, sm, bias, cg, y, qx, f);
         }
+        PAIG_STAMP(tm, 3);
     } else {
         // the planner guarantees nitems <= kFusedThreads here: accumulators persist across the channel chunks
         const bool active = tid < nitems;
@@ -216,38 +299,51 @@ __device__ __forceinline__ void run_conv(const FusedOp& op, float* sm, int f, in
         for (int c = 0; c < CO; ++c)
 #pragma unroll
             for (int p = 0; p < 4; ++p) acc[c][p] = 0.f;
-        const int S = op.S, Si = S / 2;
-        const Geo gl = geo_of(Si);
+        const int S = op.S;
+        const Geo gl = geo_of(S / 2);
         float* chunk = sm + op.chunk;
         zero_halo_planes(chunk, op.up, g, tid, kFusedThreads);
+        long long t_up = 0, t_acc = 0, t_a = 0, t_b = 0;
+        (void)t_a; (void)t_b;
         for (int c0 = 0; c0 < op.Cin0; c0 += op.up) {
             const int nch = min(op.up, op.Cin0 - c0);
-            // 2x bilinear, align_corners=False: W pass then H pass (conv.cu upsample2_kernel, same arithmetic)
-            for (int e = tid; e < nch * S * S; e += kFusedThreads) {
-                const int x = e % S, yy = (e / S) % S, c = e / (S * S);
-                int xa, xb, ya, yb;
-                float wxa, wxb, wya, wyb;
-                up_taps_f(x, Si, xa, xb, wxa, wxb);
-                up_taps_f(yy, Si, ya, yb, wya, wyb);
-                const float* p = sm + op.in0 + (c0 + c) * gl.plane + gl.P + 1;      // interior origin
-                const float top = wxa * p[ya * gl.P + xa] + wxb * p[ya * gl.P + xb];
-                const float bot = wxa * p[yb * gl.P + xa] + wxb * p[yb * gl.P + xb];
-                const float v = wya * top + wyb * bot;
-                chunk[c * g.plane + (yy + 1) * g.P + x + 1] = v;
-                if (op.gup) op.gup[(long)f * op.gup_bs + ((long)(c0 + c) * S + yy) * S + x] = v;
-            }
+#ifndef PAIG_EMU
+            if (tm) t_a = clock64();
+#endif
+            upsample_chunk(sm + op.in0 + c0 * gl.plane, gl, chunk, g, nch,
+                           op.gup ? op.gup + (long)f * op.gup_bs + (long)c0 * S * S : nullptr, tid);
             __syncthreads();
-            if (active) conv_accumulate<CO>(acc, chunk, nch, g, w + c0 * 9 * op.Cout + cg * CO, op.Cout, y, qx);
+#ifndef PAIG_EMU
+            if (tm) { t_b = clock64(); t_up += t_b - t_a; }
+#endif
+            if (active) conv_accumulate<CO, COUT>(acc, chunk, nch, g, w + c0 * 9 * COUT + cg * CO, y, qx);
             __syncthreads();
+#ifndef PAIG_EMU
+            if (tm) t_acc += clock64() - t_b;
+#endif
         }
+        if (tm) { tm[2] = t_up; tm[3] = t_acc; }
         if (active) conv_epilogue<CO>(acc, op, g, sm, bias, cg, y, qx, f);
     }
+}
+
+template <int COUT>
+__device__ __forceinline__ void run_conv_co(const FusedOp& op, float* sm, int f, int tid, long long* tm) {
+    if (COUT >= 16 && op.co_tile == 16) run_conv<(COUT >= 16 ? 16 : 4), COUT>(op, sm, f, tid, tm);
+    else if (op.co_tile == 8) run_conv<8, COUT>(op, sm, f, tid, tm);
+    else run_conv<4, COUT>(op, sm, f, tid, tm);
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const FusedPlan P) {
     PAIG_DYN_SMEM(float, sm);
     __shared__ unsigned long long bars[2];
+    __shared__ FusedOp s_ops[kFusedMaxOps];      // indexed kernel-parameter reads are constant-cache loads: copy once
     const int tid = threadIdx.x;
+    {
+        const int* src = reinterpret_cast<const int*>(P.ops);
+        int* dst = reinterpret_cast<int*>(s_ops);
+        for (int e = tid; e < (int)(P.nops * sizeof(FusedOp) / sizeof(int)); e += kFusedThreads) dst[e] = src[e];
+    }
 #ifndef PAIG_EMU
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[0])));
@@ -261,7 +357,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const 
     const int HW = P.H * P.H;
     for (int f = blockIdx.x; f < P.N; f += gridDim.x) {
         if (tid == 0 && P.first_w >= 0) {
-            const FusedOp& o = P.ops[P.first_w];
+            const FusedOp& o = s_ops[P.first_w];
             bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
         }
         // ---- the input frame, zero halo ----
@@ -283,20 +379,28 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const 
             }
         }
         __syncthreads();
+#ifndef PAIG_EMU
+        if (P.timing && tid == 0 && f == blockIdx.x + gridDim.x) P.timing[(long)blockIdx.x * 160] = clock64();
+#endif
         for (int t = 0; t < P.nops; ++t) {
-            const FusedOp& op = P.ops[t];
+            const FusedOp op = s_ops[t];
             if (tid == 0 && op.next_w >= 0) {
-                const FusedOp& o = P.ops[op.next_w];
+                const FusedOp& o = s_ops[op.next_w];
                 bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
             }
+            long long* tm = nullptr;
+#ifndef PAIG_EMU
+            if (P.timing && tid == 0 && f == blockIdx.x + gridDim.x) tm = P.timing + (long)blockIdx.x * 160 + 32 + t * 4;
+#endif
             if (op.wfloats) {
                 if (op.wbar == 0) { bulk_wait(&bars[0], phase0); phase0 ^= 1u; }
                 else { bulk_wait(&bars[1], phase1); phase1 ^= 1u; }
             }
+            PAIG_STAMP(tm, 0);
             if (op.kind == F_CONV) {
-                if (op.co_tile == 16) run_conv<16>(op, sm, f, tid);
-                else if (op.co_tile == 8) run_conv<8>(op, sm, f, tid);
-                else run_conv<4>(op, sm, f, tid);
+                if (op.Cout == 8) run_conv_co<8>(op, sm, f, tid, tm);
+                else if (op.Cout == 16) run_conv_co<16>(op, sm, f, tid, tm);
+                else run_conv_co<32>(op, sm, f, tid, tm);
             } else if (op.kind == F_POOL) {
                 const int So = op.S, C = op.Cin0;
                 const Geo go = geo_of(So), gi = geo_of(2 * So);
@@ -325,6 +429,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const 
                 }
             }
             __syncthreads();
+#ifndef PAIG_EMU
+            if (P.timing && tid == 0 && f == blockIdx.x + gridDim.x) P.timing[(long)blockIdx.x * 160 + 1 + t] = clock64();
+#endif
         }
     }
 }
@@ -516,7 +623,7 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
                 K.Cout[nl] = fo.Cout; K.Cin[nl] = cin; K.taps[nl] = taps; K.off[nl] = woff;
                 ++nl;
                 woff += (long)align64((size_t)cin * taps * fo.Cout + fo.Cout);
-                if (fo.kind == F_CONV && (fo.Cout % 4) != 0) { ok = false; break; }
+                if (fo.kind == F_CONV && fo.Cout != 8 && fo.Cout != 16 && fo.Cout != 32) { ok = false; break; }
             }
             if (op.kind == OP_HEAD) {
                 fo.gout = ws + L.logits;
@@ -619,9 +726,41 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
         int rc = check_launch("pack_weights");
         if (rc) return rc;
         int grid = L.N < sm_count() ? L.N : sm_count();
+#ifndef PAIG_EMU
+        static long long* timing_buf = nullptr;
+        if (debug && !timing_buf) cudaMalloc(&timing_buf, (size_t)sm_count() * 160 * sizeof(long long));
+        P.timing = debug ? timing_buf : nullptr;
+#endif
         launch(unet_fused_fwd_kernel, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
         (void)t;
-        return check_launch("unet_fused_fwd");
+        rc = check_launch("unet_fused_fwd");
+#ifndef PAIG_EMU
+        if (debug && !rc && L.N >= 2 * grid) {          // cycles per op, second frame of every CTA, mean over CTAs
+            cudaStreamSynchronize(st);
+            static long long host[160 * 160];
+            cudaMemcpy(host, timing_buf, (size_t)grid * 160 * sizeof(long long), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[paig] fused UNet cycles per op (mean over %d CTAs):", grid);
+            double total = 0;
+            for (int k = 0; k < nf; ++k) {
+                double s = 0;
+                for (int b = 0; b < grid; ++b) s += (double)(host[b * 160 + 1 + k] - host[b * 160 + k]);
+                fprintf(stderr, " op%d=%.0f", k, s / grid);
+                total += s / grid;
+            }
+            fprintf(stderr, " total=%.0f\n", total);
+            fprintf(stderr, "[paig]   thread 0 of CTA 0: op: wait | halo | compute | epilogue | sync\n");
+            for (int k = 0; k < nf; ++k) {
+                const long long* tmh = host + 32 + k * 4;
+                if (P.ops[k].kind == F_CONV && P.ops[k].up)
+                    fprintf(stderr, "[paig]   op%-2d (up) wait %lld | halo %lld | upsample total %lld | accumulate total %lld\n", k,
+                            tmh[0] - host[k], tmh[1] - tmh[0], tmh[2], tmh[3]);
+                if (P.ops[k].kind == F_CONV && !P.ops[k].up)
+                    fprintf(stderr, "[paig]   op%-2d %6lld | %6lld | %6lld | %6lld | %6lld\n", k, tmh[0] - host[k], tmh[1] - tmh[0],
+                            tmh[2] - tmh[1], tmh[3] - tmh[2], host[1 + k] - tmh[3]);
+            }
+        }
+#endif
+        return rc;
     }
     return -1;
 }

@@ -66,6 +66,7 @@ int lane_id();
 #define gridDim (::emu::g_gridDim)
 #define warpSize 32
 
+static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline void __syncthreads() { emu::syncthreads(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::syncwarp(); }
 
