@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(256) conv1x1_bwd_kernel(const float* __restric
                         aw[o][c] += g[o] * v;
                         d += w[o * Cin + c] * g[o];
                     }
-                din[(long)f * din_bs + (long)c * HW + p] = d;
+                if (din) din[(long)f * din_bs + (long)c * HW + p] = d;
             }
         }
     }

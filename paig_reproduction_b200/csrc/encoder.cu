@@ -236,10 +236,43 @@ static int unet_forward(const paig_task* t, const paig_params* p, const Layout& 
     return 0;
 }
 
-static int unet_backward(const paig_params* p, const paig_params* g, const Layout& L, float* ws, const float* frames,
-                         cudaStream_t st) {
+static int unet_backward(const paig_task* t, const paig_params* p, const paig_params* g, const Layout& L, float* ws,
+                         const float* frames, cudaStream_t st) {
     const Dims& d = L.d;
     float* partials = ws + L.partials;
+    // Data gradients of the whole UNet in one persistent kernel (unet_fused.cu) when it fits on chip: every conv
+    // output's ReLU-gated gradient lands in the workspace; what remains per layer is its weight gradient.
+    static const bool layerwise = getenv("PAIG_UNET_LAYERWISE") != nullptr;
+    int frc = layerwise ? -1 : unet_fused_backward(t, p, L, ws, st);
+    if (frc > 0) return frc;
+    if (frc == 0) {
+        for (int i = L.unet.nops - 1; i >= 0; --i) {
+            const Op& op = L.unet.ops[i];
+            int rc = 0;
+            if (op.kind == OP_HEAD) {
+                View v = view_of(L, ws, op.in, false);
+                rc = conv1x1_backward(v.p, v.bs, op.in.C, p->conv[op.layer].w, ws + L.d_logits, (long)d.n * d.HW,
+                                      op.relu ? ws + L.logits : nullptr, (long)d.n * d.HW, d.n, d.H, L.N, nullptr, 0,
+                                      g->conv[op.layer].w, g->conv[op.layer].b, partials, st);
+            } else if (op.kind == OP_CONV) {
+                View o = view_of(L, ws, op.out, false), go = view_of(L, ws, op.out, true);
+                WgradArgs w;
+                if (op.in.buf == -1) {
+                    w.in = frames; w.in_bs = d.CHW;
+                } else {
+                    View v = view_of(L, ws, op.in, false);
+                    w.in = v.p; w.in_bs = v.bs;
+                }
+                w.Cin = op.in.C;
+                w.g = go.p; w.g_bs = go.bs; w.Cout = op.out.C;       // already gated by the layer's ReLU
+                w.act = nullptr;
+                w.S = o.S; w.N = L.N; w.partials = partials;
+                rc = conv3x3_wgrad(w, g->conv[op.layer].w, g->conv[op.layer].b, st);
+            }
+            if (rc) return rc;
+        }
+        return 0;
+    }
     for (int i = L.unet.nops - 1; i >= 0; --i) {
         const Op& op = L.unet.ops[i];
         int rc = 0;
@@ -504,7 +537,7 @@ int encoder_backward(const paig_task* t, const paig_params* p, const paig_params
     }
     if (rc) return rc;
     const float* frames = seq_stride != (long)fps * d.CHW ? ws + L.frames : x;   // gathered by encoder_forward
-    return unet_backward(p, g, L, ws, frames, st);
+    return unet_backward(t, p, g, L, ws, frames, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -59,6 +59,7 @@ Layout make_layout(const paig_task* t, int B);
 size_t unet_wpack_floats(const UNetDesc& u, const paig_task* t);
 int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride, int fps,
                        float* ws, cudaStream_t st);
+int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st);
 
 // encoder.cu
 int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride,

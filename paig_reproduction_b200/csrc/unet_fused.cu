@@ -21,6 +21,7 @@
 #include "layout.h"
 
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -30,18 +31,24 @@ constexpr int kFusedThreads = 512;
 constexpr int kFusedMaxOps = 24;
 constexpr size_t kFusedSmemLimit = 227 * 1024 - 4096;   // dynamic part; the op table and barriers are static
 
-enum { F_CONV = 0, F_POOL = 1, F_HEAD = 2 };
+enum { F_CONV = 0, F_POOL = 1, F_HEAD = 2, F_UPT = 3, F_POOLT = 4, F_HEADT = 5 };
 
 struct FusedOp {
     int kind, S, Cin0, Cin1, Cout, relu;
     int up;                        // >0: segment 0 is the 2x upsample of a half-resolution buffer, built `up` channels at a time
     int co_tile;                   // output channels per thread: 4, 8 or 16
+    int py_tile;                   // output rows per thread: 1 or 2 (x 4 pixels)
     int in0, in1, out, chunk;      // shared-memory offsets (floats); out < 0: result is not read on chip
     int wsm, wfloats, wbar;        // weights: shared offset, packed floats (incl. bias), mbarrier index
     int next_w;                    // index of the next op that has weights (prefetched while this op runs), or -1
     long wglob;                    // offset of this layer in the packed weight buffer
     float* gout; long gout_bs;     // global destination of the result (kept for backward)
     float* gup; long gup_bs;       // global destination of the upsampled input
+    // backward-data pass (unet_fused_bwd_kernel): transposed convs reuse F_CONV with bias = 0 and a ReLU mask
+    int bias;                      // weights are followed by a bias vector
+    const float* gmask; long gmask_bs;    // activation whose sign gates the result (ReLU adjoint); F_POOLT: the pooled tensor's source
+    const float* gsrc; long gsrc_bs;      // F_HEADT: upstream gradient of the logits
+    const float* gmask2; long gmask2_bs;  // F_HEADT: the logits (head ReLU), nullable
 };
 struct FusedPlan {
     int nops, N, fps, H, first_w;
@@ -123,29 +130,24 @@ __device__ __forceinline__ void zero_halo_planes(float* base, int C, const Geo g
     }
 }
 
-// acc[c][p] += sum_{ci < nci} sum_taps w[ci][tap][c] * in[ci][y + ky - 1][4 qx + p + kx - 1]
-// COUT is a template parameter so that every weight load is [pointer + immediate]; the three row pointers advance
-// by one plane per input channel.
-template <int CO, int COUT>
-__device__ __forceinline__ void conv_accumulate(float (&acc)[CO][4], const float* __restrict__ planes, int nci,
+// acc[r][c][p] += sum_{ci < nci} sum_taps w[ci][tap][c] * in[ci][y + r + ky - 1][4 qx + p + kx - 1]
+// A thread owns PY rows x 4 pixels x CO output channels.  COUT is a template parameter so that every weight load is
+// [pointer + immediate]; the row pointer advances by one plane per input channel.  Shared-memory traffic per input
+// channel is (PY+2) x (16 B + 8 B) of pixels and 9 x CO x 4 B of (broadcast) weights for 36 x CO x PY FMAs: the
+// taller tile halves the wavefronts per FMA, which is what bounds the 4 x 1 tile (profiles/r1d_fusedfwd_*).
+template <int CO, int COUT, int PY>
+__device__ __forceinline__ void conv_accumulate(float (&acc)[PY][CO][4], const float* __restrict__ planes, int nci,
                                                 const Geo g, const float* __restrict__ w, int y, int qx) {
     const float* r0 = planes + y * g.P + 4 * qx;
-    const float* r1 = r0 + g.P;
-    const float* r2 = r1 + g.P;
-    const int plane = g.plane;
+    const int plane = g.plane, P = g.P;
 #pragma unroll 2
     for (int ci = 0; ci < nci; ++ci) {
-        float v[3][6];
-        {
-            const float4 a4 = *reinterpret_cast<const float4*>(r0);
-            const float2 a2 = *reinterpret_cast<const float2*>(r0 + 4);
-            const float4 b4 = *reinterpret_cast<const float4*>(r1);
-            const float2 b2 = *reinterpret_cast<const float2*>(r1 + 4);
-            const float4 c4 = *reinterpret_cast<const float4*>(r2);
-            const float2 c2 = *reinterpret_cast<const float2*>(r2 + 4);
-            v[0][0] = a4.x; v[0][1] = a4.y; v[0][2] = a4.z; v[0][3] = a4.w; v[0][4] = a2.x; v[0][5] = a2.y;
-            v[1][0] = b4.x; v[1][1] = b4.y; v[1][2] = b4.z; v[1][3] = b4.w; v[1][4] = b2.x; v[1][5] = b2.y;
-            v[2][0] = c4.x; v[2][1] = c4.y; v[2][2] = c4.z; v[2][3] = c4.w; v[2][4] = c2.x; v[2][5] = c2.y;
+        float v[PY + 2][6];
+#pragma unroll
+        for (int r = 0; r < PY + 2; ++r) {
+            const float4 a4 = *reinterpret_cast<const float4*>(r0 + r * P);
+            const float2 a2 = *reinterpret_cast<const float2*>(r0 + r * P + 4);
+            v[r][0] = a4.x; v[r][1] = a4.y; v[r][2] = a4.z; v[r][3] = a4.w; v[r][4] = a2.x; v[r][5] = a2.y;
         }
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky)
@@ -156,12 +158,14 @@ __device__ __forceinline__ void conv_accumulate(float (&acc)[CO][4], const float
                     const float4 w4 = *reinterpret_cast<const float4*>(w + (ky * 3 + kx) * COUT + c4);
                     const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-                    for (int c = 0; c < 4; ++c)
+                    for (int r = 0; r < PY; ++r)
 #pragma unroll
-                        for (int p = 0; p < 4; ++p) acc[c4 + c][p] += wv[c] * v[ky][kx + p];
+                        for (int c = 0; c < 4; ++c)
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) acc[r][c4 + c][p] += wv[c] * v[r + ky][kx + p];
                 }
             }
-        r0 += plane; r1 += plane; r2 += plane;
+        r0 += plane;
         w += 9 * COUT;
     }
 }
@@ -172,20 +176,34 @@ __device__ __forceinline__ void up_taps_f(int o, int Si, int& i0, int& i1, float
     else { i0 = max(k - 1, 0); i1 = k; w0 = 0.25f; w1 = 0.75f; }
 }
 
-template <int CO>
-__device__ __forceinline__ void conv_epilogue(const float (&acc)[CO][4], const FusedOp& op, const Geo g, float* sm,
-                                              const float* bias, int cg, int y, int qx, int f) {
+template <int CO, int PY>
+__device__ __forceinline__ void conv_epilogue(const float (&acc)[PY][CO][4], const FusedOp& op, const Geo g, float* sm,
+                                              const float* bias, int cg, int y0, int qx, int f) {
     const int S = g.S, x0 = 4 * qx;
     const bool vec = (S & 3) == 0;
 #pragma unroll
+    for (int r = 0; r < PY; ++r)
+#pragma unroll
     for (int c = 0; c < CO; ++c) {
-        const int co = cg * CO + c;
-        const float b = bias[co];
+        const int co = cg * CO + c, y = y0 + r;
+        const float b = op.bias ? bias[co] : 0.f;
         float o[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            o[p] = acc[c][p] + b;
+            o[p] = acc[r][c][p] + b;
             if (op.relu) o[p] = fmaxf(o[p], 0.f);
+        }
+        if (op.gmask) {                       // ReLU adjoint: pass the gradient where the forward activation was positive
+            const float* m = op.gmask + (long)f * op.gmask_bs + ((long)co * S + y) * S + x0;
+            if (vec) {
+                const float4 m4 = *reinterpret_cast<const float4*>(m);
+                o[0] = m4.x > 0.f ? o[0] : 0.f; o[1] = m4.y > 0.f ? o[1] : 0.f;
+                o[2] = m4.z > 0.f ? o[2] : 0.f; o[3] = m4.w > 0.f ? o[3] : 0.f;
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p)
+                    if (x0 + p < S) o[p] = m[p] > 0.f ? o[p] : 0.f;
+            }
         }
         if (op.out >= 0) {
             float* d = sm + op.out + co * g.plane + (y + 1) * g.P + x0 + 1;
@@ -264,41 +282,46 @@ __device__ __forceinline__ void upsample_chunk(const float* __restrict__ src, co
     }
 }
 
-template <int CO, int COUT>
+template <int CO, int COUT, int PY>
 __device__ __forceinline__ void run_conv(const FusedOp& op, float* sm, int f, int tid, long long* tm) {
     const Geo g = geo_of(op.S);
-    const int nq = op.S * g.nqx, nitems = nq * (COUT / CO);
+    const int nq = (op.S / PY) * g.nqx, nitems = nq * (COUT / CO);       // PY divides S (planner)
     const float* w = sm + op.wsm;
     const float* bias = w + (op.Cin0 + op.Cin1) * 9 * COUT;
     if (op.out >= 0) zero_halo_planes(sm + op.out, COUT, g, tid, kFusedThreads);
     PAIG_STAMP(tm, 1);
+    float acc[PY][CO][4];
     if (!op.up) {
         const bool pow2 = (nq & (nq - 1)) == 0 && (g.nqx & (g.nqx - 1)) == 0;
         const int lq = 31 - __clz(nq), lx = 31 - __clz(g.nqx);
         for (int item = tid; item < nitems; item += kFusedThreads) {
-            int cg, q, y, qx;
-            if (pow2) { cg = item >> lq; q = item & (nq - 1); y = q >> lx; qx = q & (g.nqx - 1); }
-            else { cg = item / nq; q = item % nq; y = q / g.nqx; qx = q % g.nqx; }
-            float acc[CO][4];
+            int cg, q, yr, qx;
+            if (pow2) { cg = item >> lq; q = item & (nq - 1); yr = q >> lx; qx = q & (g.nqx - 1); }
+            else { cg = item / nq; q = item % nq; yr = q / g.nqx; qx = q % g.nqx; }
+            const int y = yr * PY;
 #pragma unroll
-            for (int c = 0; c < CO; ++c)
+            for (int r = 0; r < PY; ++r)
 #pragma unroll
-                for (int p = 0; p < 4; ++p) acc[c][p] = 0.f;
-            conv_accumulate<CO, COUT>(acc, sm + op.in0, op.Cin0, g, w + cg * CO, y, qx);
-            if (op.Cin1) conv_accumulate<CO, COUT>(acc, sm + op.in1, op.Cin1, g, w + op.Cin0 * 9 * COUT + cg * CO, y, qx);
+                for (int c = 0; c < CO; ++c)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) acc[r][c][p] = 0.f;
+            conv_accumulate<CO, COUT, PY>(acc, sm + op.in0, op.Cin0, g, w + cg * CO, y, qx);
+            if (op.Cin1)
+                conv_accumulate<CO, COUT, PY>(acc, sm + op.in1, op.Cin1, g, w + op.Cin0 * 9 * COUT + cg * CO, y, qx);
             PAIG_STAMP(tm, 2);
-            conv_epilogue<CO>(acc, op, g, sm, bias, cg, y, qx, f);
+            conv_epilogue<CO, PY>(acc, op, g, sm, bias, cg, y, qx, f);
         }
         PAIG_STAMP(tm, 3);
     } else {
         // the planner guarantees nitems <= kFusedThreads here: accumulators persist across the channel chunks
         const bool active = tid < nitems;
-        const int cg = active ? tid / nq : 0, q = active ? tid % nq : 0, y = q / g.nqx, qx = q % g.nqx;
-        float acc[CO][4];
+        const int cg = active ? tid / nq : 0, q = active ? tid % nq : 0, y = (q / g.nqx) * PY, qx = q % g.nqx;
 #pragma unroll
-        for (int c = 0; c < CO; ++c)
+        for (int r = 0; r < PY; ++r)
 #pragma unroll
-            for (int p = 0; p < 4; ++p) acc[c][p] = 0.f;
+            for (int c = 0; c < CO; ++c)
+#pragma unroll
+                for (int p = 0; p < 4; ++p) acc[r][c][p] = 0.f;
         const int S = op.S;
         const Geo gl = geo_of(S / 2);
         float* chunk = sm + op.chunk;
@@ -316,22 +339,27 @@ __device__ __forceinline__ void run_conv(const FusedOp& op, float* sm, int f, in
 #ifndef PAIG_EMU
             if (tm) { t_b = clock64(); t_up += t_b - t_a; }
 #endif
-            if (active) conv_accumulate<CO, COUT>(acc, chunk, nch, g, w + c0 * 9 * COUT + cg * CO, y, qx);
+            if (active) conv_accumulate<CO, COUT, PY>(acc, chunk, nch, g, w + c0 * 9 * COUT + cg * CO, y, qx);
             __syncthreads();
 #ifndef PAIG_EMU
             if (tm) t_acc += clock64() - t_b;
 #endif
         }
         if (tm) { tm[2] = t_up; tm[3] = t_acc; }
-        if (active) conv_epilogue<CO>(acc, op, g, sm, bias, cg, y, qx, f);
+        if (active) conv_epilogue<CO, PY>(acc, op, g, sm, bias, cg, y, qx, f);
     }
 }
 
 template <int COUT>
 __device__ __forceinline__ void run_conv_co(const FusedOp& op, float* sm, int f, int tid, long long* tm) {
-    if (COUT >= 16 && op.co_tile == 16) run_conv<(COUT >= 16 ? 16 : 4), COUT>(op, sm, f, tid, tm);
-    else if (op.co_tile == 8) run_conv<8, COUT>(op, sm, f, tid, tm);
-    else run_conv<4, COUT>(op, sm, f, tid, tm);
+    if (op.py_tile == 2) {
+        if (op.co_tile == 8) run_conv<8, COUT, 2>(op, sm, f, tid, tm);
+        else run_conv<4, COUT, 2>(op, sm, f, tid, tm);
+    } else {
+        if (COUT >= 16 && op.co_tile == 16) run_conv<(COUT >= 16 ? 16 : 4), COUT, 1>(op, sm, f, tid, tm);
+        else if (op.co_tile == 8) run_conv<8, COUT, 1>(op, sm, f, tid, tm);
+        else run_conv<4, COUT, 1>(op, sm, f, tid, tm);
+    }
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const FusedPlan P) {
@@ -436,13 +464,182 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const 
     }
 }
 
+// ---- adjoint ops of the backward-data pass -----------------------------------------------------------------------
+// upsample adjoint (gather): input (i,j) of a 2x bilinear upsample collects outputs 2i-1..2i+2 x 2j-1..2j+2 with
+// weights (.25,.75,.75,.25), the clamped border taps folding back (conv.cu up_adj, same arithmetic).
+__device__ __forceinline__ void up_adj_f(int i, int Si, float (&w)[4]) {
+    w[0] = i > 0 ? 0.25f : 0.f;
+    w[1] = i > 0 ? 0.75f : 1.f;
+    w[2] = i < Si - 1 ? 0.75f : 1.f;
+    w[3] = i < Si - 1 ? 0.25f : 0.f;
+}
+
+__device__ __forceinline__ void run_upT(const FusedOp& op, float* sm, int f, int tid) {
+    const int Si = op.S, C = op.Cin0;
+    const Geo gi = geo_of(Si), go = geo_of(2 * Si);
+    if (op.out >= 0) zero_halo_planes(sm + op.out, C, gi, tid, kFusedThreads);
+    // a thread owns one low-resolution position and a residue class of the channels
+    const int per = Si * Si;
+    const int nsub = per < kFusedThreads ? kFusedThreads / per : 1;
+    for (int wk = tid; wk < per * nsub; wk += kFusedThreads) {
+        const int e = wk % per, sub = wk / per;
+        const int i = e / Si, j = e % Si;
+        float wy[4], wx[4];
+        up_adj_f(i, Si, wy);
+        up_adj_f(j, Si, wx);
+        // output (2i-1, 2j-1) sits at tile (2i, 2j); the halo rows/columns it may touch carry weight 0
+        const float* g0 = sm + op.in0 + (2 * i) * go.P + 2 * j;
+        for (int c = sub; c < C; c += nsub) {
+            const float* g = g0 + c * go.plane;
+            float s = 0.f;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                if (wy[a] == 0.f) continue;
+                float r = 0.f;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if (wx[b] != 0.f) r += wx[b] * g[a * go.P + b];
+                s += wy[a] * r;
+            }
+            if (op.gmask && !(op.gmask[(long)f * op.gmask_bs + ((long)c * Si + i) * Si + j] > 0.f)) s = 0.f;
+            if (op.out >= 0) sm[op.out + c * gi.plane + (i + 1) * gi.P + j + 1] = s;
+            if (op.gout) op.gout[(long)f * op.gout_bs + ((long)c * Si + i) * Si + j] = s;
+        }
+    }
+}
+
+// max-pool adjoint: each 2x2 window of the source X routes the pooled gradient to its first maximum (row-major, as
+// ATen / conv.cu maxpool2_bwd_kernel), adds the gradient that reached X through its other consumer (in1, parked
+// on chip) and applies X's own ReLU mask.  One thread per window and channel residue class; no atomics.
+__device__ __forceinline__ void run_poolT(const FusedOp& op, float* sm, int f, int tid) {
+    const int So = op.S, Si = 2 * So, C = op.Cin0;            // So: pooled side, Si: source side
+    const Geo gp = geo_of(So), gx = geo_of(Si);
+    if (op.out >= 0 && op.out != op.in1) zero_halo_planes(sm + op.out, C, gx, tid, kFusedThreads);
+    const int per = So * So;
+    const int nsub = per < kFusedThreads ? kFusedThreads / per : 1;
+    for (int wk = tid; wk < per * nsub; wk += kFusedThreads) {
+        const int e = wk % per, sub = wk / per;
+        const int y = e / So, x = e % So;
+        for (int c = sub; c < C; c += nsub) {
+            const float* xs = op.gmask + (long)f * op.gmask_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
+            const float2 a = *reinterpret_cast<const float2*>(xs);
+            const float2 b = *reinterpret_cast<const float2*>(xs + Si);
+            const float v[4] = {a.x, a.y, b.x, b.y};
+            int best = 0;
+            float m = v[0];
+            if (v[1] > m) { m = v[1]; best = 1; }
+            if (v[2] > m) { m = v[2]; best = 2; }
+            if (v[3] > m) { m = v[3]; best = 3; }
+            const float g = sm[op.in0 + c * gp.plane + (y + 1) * gp.P + x + 1];
+            const int t00 = c * gx.plane + (2 * y + 1) * gx.P + 2 * x + 1;
+            const int toff[4] = {t00, t00 + 1, t00 + gx.P, t00 + gx.P + 1};
+            const long g00 = (long)f * op.gout_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
+            const long goff[4] = {g00, g00 + 1, g00 + Si, g00 + Si + 1};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float r = op.in1 >= 0 ? sm[op.in1 + toff[k]] : 0.f;
+                if (k == best) r += g;
+                if (op.relu && !(v[k] > 0.f)) r = 0.f;
+                if (op.out >= 0) sm[op.out + toff[k]] = r;
+                if (op.gout) op.gout[goff[k]] = r;
+            }
+        }
+    }
+}
+
+// 1x1 head adjoint: d in[c] = sum_o w[o][c] * g[o], g = d logits gated by the head's own ReLU; result gated by the
+// ReLU of the layer that produced `in`.
+__device__ __forceinline__ void run_headT(const FusedOp& op, float* sm, int f, int tid) {
+    const int S = op.S, C = op.Cout, NO = op.Cin0;            // C: channels of the head's input, NO: logits
+    const Geo g = geo_of(S);
+    const float* w = sm + op.wsm;                             // [NO][C]
+    if (op.out >= 0) zero_halo_planes(sm + op.out, C, g, tid, kFusedThreads);
+    for (int e = tid; e < S * S; e += kFusedThreads) {
+        const int y = e / S, x = e % S;
+        float gl[kMaxObjs];
+#pragma unroll
+        for (int o = 0; o < kMaxObjs; ++o) {
+            gl[o] = 0.f;
+            if (o < NO) {
+                gl[o] = op.gsrc[(long)f * op.gsrc_bs + (long)o * S * S + e];
+                if (op.gmask2 && !(op.gmask2[(long)f * op.gmask2_bs + (long)o * S * S + e] > 0.f)) gl[o] = 0.f;
+            }
+        }
+        for (int c = 0; c < C; ++c) {
+            float d = 0.f;
+#pragma unroll
+            for (int o = 0; o < kMaxObjs; ++o)
+                if (o < NO) d += w[o * C + c] * gl[o];
+            if (op.gmask && !(op.gmask[(long)f * op.gmask_bs + (long)c * S * S + e] > 0.f)) d = 0.f;
+            if (op.out >= 0) sm[op.out + c * g.plane + (y + 1) * g.P + x + 1] = d;
+            if (op.gout) op.gout[(long)f * op.gout_bs + (long)c * S * S + e] = d;
+        }
+    }
+}
+
+// Backward-data pass of the whole UNet for one frame at a time: the gradient of every conv output, already gated by
+// that layer's ReLU, goes to the workspace (where the weight-gradient kernels read it) and stays on chip for the
+// next transposed conv.  Same CTA shape, planner and weight pipeline as the forward kernel.
+__global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_bwd_kernel(const FusedPlan P) {
+    PAIG_DYN_SMEM(float, sm);
+    __shared__ unsigned long long bars[2];
+    __shared__ FusedOp s_ops[kFusedMaxOps];
+    const int tid = threadIdx.x;
+    {
+        const int* src = reinterpret_cast<const int*>(P.ops);
+        int* dst = reinterpret_cast<int*>(s_ops);
+        for (int e = tid; e < (int)(P.nops * sizeof(FusedOp) / sizeof(int)); e += kFusedThreads) dst[e] = src[e];
+    }
+#ifndef PAIG_EMU
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&bars[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
+    __syncthreads();
+    unsigned phase0 = 0, phase1 = 0;
+    for (int f = blockIdx.x; f < P.N; f += gridDim.x) {
+        if (tid == 0 && P.first_w >= 0) {
+            const FusedOp& o = s_ops[P.first_w];
+            bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
+        }
+        for (int t = 0; t < P.nops; ++t) {
+            const FusedOp op = s_ops[t];
+            if (tid == 0 && op.next_w >= 0) {
+                const FusedOp& o = s_ops[op.next_w];
+                bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
+            }
+            if (op.wfloats) {
+                if (op.wbar == 0) { bulk_wait(&bars[0], phase0); phase0 ^= 1u; }
+                else { bulk_wait(&bars[1], phase1); phase1 ^= 1u; }
+            }
+            if (op.kind == F_CONV) {
+                if (op.Cout == 8) run_conv_co<8>(op, sm, f, tid, nullptr);
+                else if (op.Cout == 16) run_conv_co<16>(op, sm, f, tid, nullptr);
+                else run_conv_co<32>(op, sm, f, tid, nullptr);
+            } else if (op.kind == F_UPT) {
+                run_upT(op, sm, f, tid);
+            } else if (op.kind == F_POOLT) {
+                run_poolT(op, sm, f, tid);
+            } else {
+                run_headT(op, sm, f, tid);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // ---- weight packing: [co][ci][tap] -> [ci][tap][co] | bias  (head: [co][ci] | bias kept as is) ----------------
 struct PackPlan {
     int nlayers;
-    const float* w[18];
-    const float* b[18];
-    int Cout[18], Cin[18], taps[18];
-    long off[18];
+    const float* w[24];
+    const float* b[24];
+    int Cout[24], Cin[24], taps[24];
+    int mode[24];      // 0: forward [ci][tap][co] | bias.  1: transposed slice for the backward-data pass:
+                       //    dst[(co*9 + tap)*Cout + c] = W[co][ci0 + c][8 - tap]   (Cin = number of co, no bias)
+    int ci0[24], cin_total[24];
+    long off[24];
 };
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackPlan P, float* __restrict__ dst) {
     const int l = blockIdx.y;
@@ -450,6 +647,17 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackPlan P, flo
     const int Cout = P.Cout[l], Cin = P.Cin[l], taps = P.taps[l];
     const int nW = Cout * Cin * taps;
     float* d = dst + P.off[l];
+    if (P.mode[l] == 2) {                                    // head weights as they are, no bias
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nW; e += gridDim.x * blockDim.x) d[e] = P.w[l][e];
+        return;
+    }
+    if (P.mode[l] == 1) {
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nW; e += gridDim.x * blockDim.x) {
+            const int c = e % Cout, tap = (e / Cout) % 9, co = e / (Cout * 9);
+            d[e] = P.w[l][((long)co * P.cin_total[l] + P.ci0[l] + c) * 9 + (8 - tap)];
+        }
+        return;
+    }
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nW + Cout; e += gridDim.x * blockDim.x) {
         if (e >= nW) {
             d[e] = P.b[l][e - nW];
@@ -509,6 +717,45 @@ struct Planner {
     }
 };
 
+
+// Thread tile of a conv: CO output channels x PY rows x 4 pixels.  Cost model per input channel, for the busiest
+// SM sub-partition: FMA issue slots vs shared-memory wavefronts (measured: 16-byte pixel load 4, 8-byte 4 (2-way
+// conflict), broadcast 16-byte weight load 2), with a penalty when too few warps remain to hide latency.
+bool choose_tile(FusedOp& fo, bool single_pass) {
+    static const char* force = getenv("PAIG_TILE");          // "co,py": experiments
+    int fco = 0, fpy = 0;
+    if (force) sscanf(force, "%d,%d", &fco, &fpy);
+    const Geo g = geo_of(fo.S);
+    double best_cost = 0;
+    int best_co = 0, best_py = 0;
+    for (int py = 1; py <= 2; ++py) {
+        if (fo.S % py) continue;
+        for (int co = 4; co <= 16; co *= 2) {
+            if (fo.Cout % co || (py == 2 && co == 16)) continue;
+            const int items = (fo.S / py) * g.nqx * (fo.Cout / co);
+            const int passes = (items + kFusedThreads - 1) / kFusedThreads;
+            if (single_pass && passes > 1) continue;
+            const int warps = ((items < kFusedThreads ? items : kFusedThreads) + 31) / 32;
+            // Calibrated on B200 (per-op cycle stamps, PAIG_DEBUG): an op takes (instructions issued by the busiest
+            // sub-partition) / IPC, with IPC 0.55 / 0.67 / 0.75 / 0.80 at 1 / 2 / 3 / >=4 resident warps; the
+            // shared-memory pipe (one wavefront per cycle per SM) is the second bound.
+            const int wps = (warps + 3) / 4;
+            const double per_warp = 36.0 * co * py + (py + 2) * 2 + 9 * co / 4 + 6;
+            const double ipc = wps >= 4 ? 0.80 : (wps == 3 ? 0.75 : (wps == 2 ? 0.67 : 0.55));
+            const double issue = (double)passes * wps * per_warp / ipc;
+            const double lsu = (double)passes * warps * ((py + 2) * 8 + 9 * co / 4 * 2);
+            double cost = issue > lsu ? issue : lsu;
+            const bool forced = co == fco && py == fpy;
+            if (forced) cost = 1.0;
+            if (!best_co || cost < best_cost) { best_cost = cost; best_co = co; best_py = py; }
+        }
+    }
+    if (!best_co) return false;
+    fo.co_tile = best_co;
+    fo.py_tile = best_py;
+    return true;
+}
+
 int sm_count() {
 #ifdef PAIG_EMU
     return 2;
@@ -528,13 +775,13 @@ int sm_count() {
 
 size_t unet_wpack_floats(const UNetDesc& u, const paig_task* t) {
     (void)t;
-    size_t total = 0;
+    size_t total = 24 * 64;      // forward and backward-data packings, each entry padded to 256 bytes
     for (int i = 0; i < u.nops; ++i) {
         const Op& op = u.ops[i];
         if (op.kind == OP_CONV) total += align64((size_t)op.in.C * 9 * op.out.C + op.out.C);
         else if (op.kind == OP_HEAD) total += align64((size_t)op.in.C * op.out.C + op.out.C);
     }
-    return total;
+    return 2 * total;
 }
 
 // Returns 0 on success, 1 on error, -1 when the network does not fit on chip (caller uses the per-layer path).
@@ -619,6 +866,7 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
                 const int cin = fo.Cin0 + fo.Cin1;
                 fo.wfloats = (cin * taps * fo.Cout + fo.Cout + 3) & ~3;
                 fo.wglob = woff;
+                fo.bias = 1;
                 K.w[nl] = p->conv[op.layer].w; K.b[nl] = p->conv[op.layer].b;
                 K.Cout[nl] = fo.Cout; K.Cin[nl] = cin; K.taps[nl] = taps; K.off[nl] = woff;
                 ++nl;
@@ -642,27 +890,8 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
         K.nlayers = nl;
         P.nops = nf;
         // ---- 2. thread tiling of each conv ----
-        for (int k = 0; k < nf; ++k) {
-            FusedOp& fo = P.ops[k];
-            if (fo.kind != F_CONV) continue;
-            const Geo g = geo_of(fo.S);
-            const int nq = fo.S * g.nqx;
-            int best = 0;
-            long best_cost = 0;
-            const int cands[3] = {8, 4, 16};
-            for (int ci = 0; ci < 3; ++ci) {
-                const int co = cands[ci];
-                if (fo.Cout % co) continue;
-                const int items = nq * (fo.Cout / co);
-                const int passes = (items + kFusedThreads - 1) / kFusedThreads;
-                if (fo.up && passes > 1) continue;
-                // issue slots per input channel: passes x (36*co FMA + 6 + 9*co/4 loads) for the busiest thread
-                const long cost = (long)passes * (36 * co + 6 + 9 * co / 4);
-                if (!best || cost < best_cost) { best = co; best_cost = cost; }
-            }
-            if (!best) return -1;
-            fo.co_tile = best;
-        }
+        for (int k = 0; k < nf; ++k)
+            if (P.ops[k].kind == F_CONV && !choose_tile(P.ops[k], P.ops[k].up != 0)) return -1;
         // ---- 3. weight prefetch chain + barriers ----
         int prev = -1, widx = 0;
         P.first_w = -1;
@@ -712,8 +941,8 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
                     (size_t)peak * sizeof(float));
             for (int k = 0; k < nf; ++k) {
                 const FusedOp& fo = P.ops[k];
-                fprintf(stderr, "[paig]   op%-2d kind=%d S=%-2d Cin=%d+%d Cout=%-2d up=%d co=%-2d in0=%d in1=%d out=%d chunk=%d w@%d(%d)\n",
-                        k, fo.kind, fo.S, fo.Cin0, fo.Cin1, fo.Cout, fo.up, fo.co_tile, fo.in0, fo.in1, fo.out, fo.chunk,
+                fprintf(stderr, "[paig]   op%-2d kind=%d S=%-2d Cin=%d+%d Cout=%-2d up=%d co=%-2d py=%d in0=%d in1=%d out=%d chunk=%d w@%d(%d)\n",
+                        k, fo.kind, fo.S, fo.Cin0, fo.Cin1, fo.Cout, fo.up, fo.co_tile, fo.py_tile, fo.in0, fo.in1, fo.out, fo.chunk,
                         fo.wsm, fo.wfloats);
             }
         }
@@ -763,6 +992,241 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
         return rc;
     }
     return -1;
+}
+
+// Offset (floats) where the backward-data packing starts inside the wpack region.
+static long wpack_bwd_base(const UNetDesc& u) { return (long)(unet_wpack_floats(u, nullptr) / 2); }
+
+// Backward-data pass of the UNet in one persistent kernel.  Expects d_logits in the workspace; writes the ReLU-gated
+// gradient of every conv output into the workspace gradient buffers (what conv3x3_wgrad reads).  Returns -1 when
+// the network or its pattern of skip connections is not supported (caller runs the per-layer kernels).
+int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st) {
+    const UNetDesc& u = L.unet;
+    const Dims& d = L.d;
+    FusedPlan P;
+    memset(&P, 0, sizeof(P));
+    PackPlan K;
+    memset(&K, 0, sizeof(K));
+
+    // forward facts: who produced each slice, with a ReLU or not, and how many ops read it
+    struct Prod { int buf, c0, C, op, kind, relu, readers; };
+    Prod pr[40];
+    int npr = 0;
+    for (int i = 0; i < u.nops; ++i) {
+        const Op& op = u.ops[i];
+        if (op.kind == OP_HEAD) continue;
+        pr[npr++] = Prod{op.out.buf, op.out.c0, op.out.C, i, op.kind, op.relu, 0};
+    }
+    auto prod_of = [&](int buf, int c0, int C) -> int {
+        for (int k = 0; k < npr; ++k)
+            if (pr[k].buf == buf && pr[k].c0 == c0 && pr[k].C == C) return k;
+        return -1;
+    };
+    auto prods_in = [&](const Ref& r, int* a, int* b) {          // producer slices tiling the range r, by channel
+        *a = *b = -1;
+        for (int k = 0; k < npr; ++k) {
+            if (pr[k].buf != r.buf || pr[k].c0 < r.c0 || pr[k].c0 + pr[k].C > r.c0 + r.C) continue;
+            if (*a < 0) *a = k;
+            else if (*b < 0) { if (pr[k].c0 < pr[*a].c0) { *b = *a; *a = k; } else *b = k; }
+            else return false;
+        }
+        if (*a < 0) return false;
+        return pr[*a].C + (*b >= 0 ? pr[*b].C : 0) == r.C && pr[*a].c0 == r.c0;
+    };
+    for (int i = 0; i < u.nops; ++i) {
+        const Op& op = u.ops[i];
+        if (op.in.buf < 0) continue;
+        int a, b;
+        if (!prods_in(op.in, &a, &b)) return -1;
+        pr[a].readers++;
+        if (b >= 0) pr[b].readers++;
+    }
+    auto side_of = [&](int buf) { return d.H >> u.bufs[buf].shift; };
+    auto act_ptr = [&](const Prod& q, long* bs) {
+        const int S = side_of(q.buf);
+        *bs = (long)u.bufs[q.buf].C * S * S;
+        return (const float*)(ws + L.act[q.buf] + (long)q.c0 * S * S);
+    };
+    auto grad_ptr = [&](const Prod& q, long* bs) {
+        const int S = side_of(q.buf);
+        *bs = (long)u.bufs[q.buf].C * S * S;
+        return ws + L.grad[q.buf] + (long)q.c0 * S * S;
+    };
+
+    // gradient slices on chip, one per producer slice
+    struct GS { int born, last, off, floats, parked; };
+    GS gs[40];
+    for (int k = 0; k < npr; ++k) gs[k] = GS{-1, -1, -1, 0, 0};
+    int in0_of[kFusedMaxOps], in1_of[kFusedMaxOps], out_of[kFusedMaxOps];
+    int nf = 0, nl = 0;
+    long woff = wpack_bwd_base(u);
+    auto new_op = [&](int kind) -> FusedOp* {
+        if (nf >= kFusedMaxOps) return nullptr;
+        FusedOp& fo = P.ops[nf];
+        memset(&fo, 0, sizeof(fo));
+        fo.kind = kind;
+        fo.out = fo.chunk = fo.in1 = -1;
+        fo.next_w = -1;
+        in0_of[nf] = in1_of[nf] = out_of[nf] = -1;
+        return &fo;
+    };
+    // result slice k of the op being emitted: final (gated + written for wgrad) or parked for a later max-pool adjoint
+    auto finish = [&](FusedOp* fo, int k, bool final_) {
+        const Prod& q = pr[k];
+        if (final_) {
+            if (q.relu) fo->gmask = act_ptr(q, &fo->gmask_bs);
+            if (q.kind == OP_CONV) fo->gout = grad_ptr(q, &fo->gout_bs);
+        }
+        if (gs[k].born < 0) gs[k].born = nf;
+        out_of[nf] = k;
+    };
+    for (int i = u.nops - 1; i >= 0; --i) {
+        const Op& op = u.ops[i];
+        if (op.kind == OP_UP) continue;                 // emitted with the conv that reads it
+        if (op.kind == OP_HEAD) {
+            int a, b;
+            if (!prods_in(op.in, &a, &b) || b >= 0 || pr[a].readers != 1) return -1;
+            FusedOp* fo = new_op(F_HEADT);
+            if (!fo) return -1;
+            fo->S = d.H; fo->Cin0 = op.out.C; fo->Cout = op.in.C;
+            fo->gsrc = ws + L.d_logits; fo->gsrc_bs = (long)d.n * d.HW;
+            if (op.relu) { fo->gmask2 = ws + L.logits; fo->gmask2_bs = (long)d.n * d.HW; }
+            fo->wfloats = (op.out.C * op.in.C + 3) & ~3;
+            fo->wglob = woff;
+            K.w[nl] = p->conv[op.layer].w; K.b[nl] = nullptr; K.Cout[nl] = op.out.C; K.Cin[nl] = op.in.C; K.taps[nl] = 1;
+            K.mode[nl] = 2; K.off[nl] = woff; ++nl;
+            woff += (long)align64((size_t)op.out.C * op.in.C);
+            finish(fo, a, true);
+            ++nf;
+            continue;
+        }
+        if (op.kind == OP_POOL) {
+            const int kp = prod_of(op.out.buf, op.out.c0, op.out.C);
+            int a, b;
+            if (kp < 0 || gs[kp].born < 0 || !prods_in(op.in, &a, &b) || b >= 0) return -1;
+            FusedOp* fo = new_op(F_POOLT);
+            if (!fo) return -1;
+            fo->S = side_of(op.out.buf); fo->Cin0 = op.out.C; fo->Cout = op.out.C;
+            fo->relu = pr[a].relu;
+            fo->gmask = act_ptr(pr[a], &fo->gmask_bs);           // source values: arg-max and ReLU gate
+            if (pr[a].kind == OP_CONV) fo->gout = grad_ptr(pr[a], &fo->gout_bs);
+            in0_of[nf] = kp; gs[kp].last = nf;
+            if (gs[a].born >= 0) { in1_of[nf] = a; gs[a].last = nf; }   // parked contribution of the other reader
+            else gs[a].born = nf;
+            out_of[nf] = a;
+            gs[a].parked = 0;
+            ++nf;
+            continue;
+        }
+        // OP_CONV
+        const int ko = prod_of(op.out.buf, op.out.c0, op.out.C);
+        if (ko < 0) return -1;
+        if (op.in.buf < 0) continue;                    // first layer: no gradient w.r.t. the frames
+        if (gs[ko].born < 0) return -1;
+        const bool via_up = i > 0 && u.ops[i - 1].kind == OP_UP && u.ops[i - 1].out.buf == op.in.buf &&
+                            u.ops[i - 1].out.c0 == op.in.c0 && u.ops[i - 1].out.C == op.in.C;
+        int a, b;
+        if (!prods_in(op.in, &a, &b)) return -1;
+        const int parts[2] = {a, b};
+        for (int part = 0; part < 2; ++part) {
+            const int k = parts[part];
+            if (k < 0) continue;
+            if (pr[k].C != 8 && pr[k].C != 16 && pr[k].C != 32) return -1;
+            FusedOp* fo = new_op(F_CONV);
+            if (!fo) return -1;
+            fo->S = side_of(op.out.buf); fo->Cin0 = op.out.C; fo->Cout = pr[k].C;
+            fo->wfloats = (op.out.C * 9 * pr[k].C + 3) & ~3;
+            fo->wglob = woff;
+            K.w[nl] = p->conv[op.layer].w; K.b[nl] = nullptr; K.Cout[nl] = pr[k].C; K.Cin[nl] = op.out.C; K.taps[nl] = 9;
+            K.mode[nl] = 1; K.ci0[nl] = pr[k].c0 - op.in.c0; K.cin_total[nl] = op.in.C; K.off[nl] = woff; ++nl;
+            woff += (long)align64((size_t)op.out.C * 9 * pr[k].C);
+            in0_of[nf] = ko; gs[ko].last = nf;
+            if (via_up) {
+                // k is the upsampled tensor: keep its gradient on chip only, then gather it back to the source
+                if (pr[k].readers != 1 || b >= 0) return -1;
+                finish(fo, k, false);
+                ++nf;
+                const Op& upo = u.ops[i - 1];
+                int ua, ub;
+                if (!prods_in(upo.in, &ua, &ub) || ub >= 0 || pr[ua].readers != 1) return -1;
+                FusedOp* fu = new_op(F_UPT);
+                if (!fu) return -1;
+                fu->S = side_of(upo.in.buf); fu->Cin0 = upo.in.C; fu->Cout = upo.in.C;
+                in0_of[nf] = k; gs[k].last = nf;
+                finish(fu, ua, true);
+                ++nf;
+            } else if (pr[k].readers == 1) {
+                finish(fo, k, true);
+                ++nf;
+            } else if (pr[k].readers == 2 && gs[k].born < 0) {
+                finish(fo, k, false);                    // parked until the max-pool adjoint adds its share
+                gs[k].parked = 1;
+                ++nf;
+            } else {
+                return -1;
+            }
+        }
+    }
+    if (nl > 24) return -1;
+    K.nlayers = nl;
+    P.nops = nf;
+    for (int k = 0; k < npr; ++k)
+        if (gs[k].parked) return -1;                     // a parked gradient nobody finalised
+    // thread tiling of the transposed convs
+    for (int k = 0; k < nf; ++k)
+        if (P.ops[k].kind == F_CONV && !choose_tile(P.ops[k], false)) return -1;
+    // weight pipeline
+    int issue_at[kFusedMaxOps];
+    {
+        int prev = -1, widx = 0;
+        P.first_w = -1;
+        for (int k = 0; k < nf; ++k) {
+            issue_at[k] = -1;
+            if (!P.ops[k].wfloats) continue;
+            P.ops[k].wbar = widx++ & 1;
+            issue_at[k] = prev;
+            if (prev < 0) P.first_w = k;
+            else P.ops[prev].next_w = k;
+            prev = k;
+        }
+    }
+    // shared-memory plan
+    Planner al;
+    for (int k = 0; k < nf; ++k)
+        if (P.ops[k].wfloats) al.add(P.ops[k].wfloats, issue_at[k], k, &P.ops[k].wsm);
+    for (int k = 0; k < npr; ++k) {
+        if (gs[k].born < 0 || gs[k].last < 0) continue;
+        gs[k].floats = pr[k].C * geo_of(side_of(pr[k].buf)).plane;
+        al.add(gs[k].floats, gs[k].born, gs[k].last, &gs[k].off);
+    }
+    const int peak = al.place();
+    for (int k = 0; k < nf; ++k) {
+        FusedOp& fo = P.ops[k];
+        if (in0_of[k] >= 0) fo.in0 = gs[in0_of[k]].off;
+        if (in1_of[k] >= 0) fo.in1 = gs[in1_of[k]].off;
+        if (out_of[k] >= 0 && gs[out_of[k]].last >= 0) fo.out = gs[out_of[k]].off;
+    }
+    static const bool debug = getenv("PAIG_DEBUG") != nullptr;
+    if (debug) {
+        fprintf(stderr, "[paig] fused UNet backward-data plan: H=%d ops=%d smem=%zu B\n", d.H, nf, (size_t)peak * sizeof(float));
+        for (int k = 0; k < nf; ++k) {
+            const FusedOp& fo = P.ops[k];
+            fprintf(stderr, "[paig]   op%-2d kind=%d S=%-2d Cin=%-2d Cout=%-2d co=%-2d in0=%d in1=%d out=%d mask=%d gout=%d w@%d(%d)\n", k,
+                    fo.kind, fo.S, fo.Cin0, fo.Cout, fo.co_tile, fo.in0, fo.in1, fo.out, fo.gmask != nullptr,
+                    fo.gout != nullptr, fo.wsm, fo.wfloats);
+        }
+    }
+    if ((size_t)peak * sizeof(float) > kFusedSmemLimit) return -1;
+    P.N = L.N; P.fps = 1; P.H = d.H;
+    float* wpack = ws + L.wpack;
+    P.wpack = wpack;
+    launch(pack_weights_kernel, dim3(4, K.nlayers), dim3(256), 0, st, K, wpack);
+    int rc = check_launch("pack_weights");
+    if (rc) return rc;
+    const int grid = L.N < sm_count() ? L.N : sm_count();
+    launch(unet_fused_bwd_kernel, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
+    (void)t;
+    return check_launch("unet_fused_bwd");
 }
 
 }  // namespace paig
