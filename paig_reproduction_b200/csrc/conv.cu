@@ -392,6 +392,10 @@ size_t wgrad_partials_floats(int Cin, int Cout) { return (size_t)kWgradMaxCtas *
 int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t st) {
     WgradArgs a = in_args;
     if (a.N <= 0) return 0;
+    {
+        const int rc = conv3x3_wgrad_tma(in_args, dW, db, st);     // TMA-staged, double-buffered strips when eligible
+        if (rc >= 0) return rc;
+    }
     const int QX = (a.S + 3) / 4, PITCH = 4 * QX + 4;
     a.in_plane = pad_plane((kWgTH + 2) * PITCH);
     a.g_plane = pad_plane(kWgTH * 4 * QX);
