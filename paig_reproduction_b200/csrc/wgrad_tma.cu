@@ -157,30 +157,34 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
             const int nq = rows * QX;
             const float* ipc = sIn + ci * a.in_plane;
             const float* gpc = sG + cob * COB * a.g_plane;
+            const int bxi = a.vin.boxx, bxg = a.vg.boxx, gpl = a.g_plane;
+            // quads q = part, part + P, ...: (row, quad-in-row) advance without a division per step
+            const int dr = P / QX, dq = P % QX;
+            int r = part / QX, qx = part % QX;
             for (int q = part; q < nq; q += P) {
-                const int r = q / QX, x0 = (q % QX) * 4;
+                const float* ip = ipc + r * bxi + 4 * qx;              // tile column = image column + 4
+                const float* gp = gpc + r * bxg + 4 * qx;
                 float v[3][6];
-                const float* ip = ipc + r * a.vin.boxx + x0;          // tile column = image column + 4
 #pragma unroll
                 for (int kk = 0; kk < 3; ++kk) {
-                    const float* row = ip + kk * a.vin.boxx;
+                    const float* row = ip + kk * bxi;
                     const float4 p4 = *reinterpret_cast<const float4*>(row + 4);
                     v[kk][0] = row[3]; v[kk][1] = p4.x; v[kk][2] = p4.y; v[kk][3] = p4.z; v[kk][4] = p4.w; v[kk][5] = row[8];
                 }
 #pragma unroll
                 for (int c = 0; c < COB; ++c) {
-                    if (cob * COB + c < a.Cout) {
-                        const float4 g4 = *reinterpret_cast<const float4*>(gpc + c * a.g_plane + r * a.vg.boxx + x0);
-                        const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
-                        bacc[c] += (gv[0] + gv[1]) + (gv[2] + gv[3]);
+                    const float4 g4 = *reinterpret_cast<const float4*>(gp + c * gpl);
+                    const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+                    bacc[c] += (gv[0] + gv[1]) + (gv[2] + gv[3]);
 #pragma unroll
-                        for (int ky = 0; ky < 3; ++ky)
+                    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-                            for (int kx = 0; kx < 3; ++kx)
+                        for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                                for (int p = 0; p < 4; ++p) acc[c][ky * 3 + kx] += gv[p] * v[ky][kx + p];
-                    }
+                            for (int p = 0; p < 4; ++p) acc[c][ky * 3 + kx] += gv[p] * v[ky][kx + p];
                 }
+                r += dr; qx += dq;
+                if (qx >= QX) { qx -= QX; ++r; }
             }
         }
         __syncthreads();                                               // everyone is done with this stage
@@ -289,6 +293,7 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
     a.g_off = (a.Cin * a.in_plane + 31) & ~31;                         // 128-byte aligned TMA destinations
     a.stage_floats = (a.g_off + a.Cout * a.g_plane + 31) & ~31;
     const int COB = (a.Cout % 8) == 0 ? 8 : 4;
+    if (a.Cout % COB) return -1;
     const int G = ((a.Cout + COB - 1) / COB) * a.Cin;
     const int gsets = cdiv(G, kWtThreads);
     const int G_per = cdiv(G, gsets);
