@@ -375,6 +375,45 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
     }
 }
 
+// the same fold for a batch of independent reductions: blockIdx.y selects the entry
+__global__ void __launch_bounds__(256) reduce_partials_batch_kernel(const ReduceBatch b) {
+    __shared__ float part[8][33];
+    const int k = blockIdx.y;
+    const int n0 = b.n0[k], n1 = b.n1[k], nparts = b.nparts[k], stride = b.stride[k];
+    const float* __restrict__ partials = b.partials[k];
+    if ((int)blockIdx.x * 32 >= n0 + n1) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (i < n0 + n1) {
+        int p = w;
+        for (; p + 24 < nparts; p += 32) {
+            s0 += partials[(size_t)p * stride + i];
+            s1 += partials[(size_t)(p + 8) * stride + i];
+            s2 += partials[(size_t)(p + 16) * stride + i];
+            s3 += partials[(size_t)(p + 24) * stride + i];
+        }
+        for (; p < nparts; p += 8) s0 += partials[(size_t)p * stride + i];
+    }
+    part[w][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (w == 0 && i < n0 + n1) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += part[j][lane];
+        if (i < n0) b.out0[k][i] = s;
+        else if (b.out1[k]) b.out1[k][i - n0] = s;
+    }
+}
+
+int reduce_partials_batch(const ReduceBatch& b, cudaStream_t st) {
+    if (b.n <= 0) return 0;
+    int widest = 0;
+    for (int k = 0; k < b.n; ++k) widest = b.n0[k] + b.n1[k] > widest ? b.n0[k] + b.n1[k] : widest;
+    launch(reduce_partials_batch_kernel, dim3(cdiv(widest, 32), b.n), dim3(256), 0, st, b);
+    return check_launch("reduce_partials");
+}
+
 int reduce_partials(const float* partials, int nparts, int stride, int n0, float* out0, int n1, float* out1,
                     cudaStream_t st) {
     launch(reduce_partials_kernel, dim3(cdiv(n0 + n1, 32)), dim3(256), 0, st, partials, nparts, stride, n0, out0, n1,
@@ -431,6 +470,7 @@ int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t s
     int rc = check_launch("conv3x3_wgrad");
     if (rc) return rc;
     const int nW = a.Cout * a.Cin * 9;
+    if (a.defer) return a.defer->add(a.partials, ctas, nW + a.Cout, nW, dW, a.Cout, db) ? 0 : 1;
     return reduce_partials(a.partials, ctas, nW + a.Cout, nW, dW, a.Cout, db, st);
 }
 
@@ -536,7 +576,7 @@ int conv1x1_forward(const float* in, long in_bs, int Cin, const float* w, const 
 
 int conv1x1_backward(const float* in, long in_bs, int Cin, const float* w, const float* dout, long dout_bs,
                      const float* act, long act_bs, int Cout, int S, int N, float* din, long din_bs, float* dW,
-                     float* db, float* partials, cudaStream_t st) {
+                     float* db, float* partials, cudaStream_t st, ReduceBatch* defer) {
     if (Cin > kMaxHeadIn || Cout > kMaxObjs) {
         set_error("conv1x1: %d->%d channels unsupported", Cin, Cout);
         return 1;
@@ -547,6 +587,7 @@ int conv1x1_backward(const float* in, long in_bs, int Cin, const float* w, const
            S * S, N, din, din_bs, partials);
     int rc = check_launch("conv1x1_bwd");
     if (rc) return rc;
+    if (defer) return defer->add(partials, blocks, Cout * Cin + Cout, Cout * Cin, dW, Cout, db) ? 0 : 1;
     return reduce_partials(partials, blocks, Cout * Cin + Cout, Cout * Cin, dW, Cout, db, st);
 }
 

@@ -127,7 +127,7 @@ Layout make_layout(const paig_task* t, int B) {
         return o;
     };
     const size_t N = (size_t)L.N, nN = (size_t)d.n * L.N, nB = (size_t)d.n * B;
-    size_t max_w = 0;
+    size_t max_w = 0, sum_w = 0;
     for (int i = 0; i < L.unet.nbufs; ++i) {
         const int S = d.H >> L.unet.bufs[i].shift;
         const size_t fl = N * L.unet.bufs[i].C * S * S;
@@ -139,10 +139,13 @@ Layout make_layout(const paig_task* t, int B) {
         if (op.kind == OP_CONV) {
             const size_t w = wgrad_partials_floats(op.in.C, op.out.C);
             max_w = w > max_w ? w : max_w;
+            sum_w += align64(w);
         }
     }
     const size_t head = (size_t)592 * (kMaxObjs * 17);
     max_w = head > max_w ? head : max_w;
+    sum_w += align64(head);                 // every layer keeps its own partials when the folds are batched
+    max_w = sum_w > max_w ? sum_w : max_w;
     L.logits = take(N * d.n * d.HW);
     L.d_logits = take(N * d.n * d.HW);
     L.masks = take(N * (d.n + 1) * d.HW);
@@ -168,7 +171,7 @@ Layout make_layout(const paig_task* t, int B) {
     L.losses = take(8);
     L.dphys = take(8);
     {   // room for the split-K partials of encoder.l1 forward ([splits][nN][200]) and weight gradient ([splits][200][K])
-        const size_t fwd = (size_t)cdiv(L.K, 512) * nN * kHidden, wg = 4 * (size_t)kHidden * L.K;
+        const size_t fwd = (size_t)cdiv(L.K, 256) * nN * kHidden, wg = 4 * (size_t)kHidden * L.K;
         const size_t sk = fwd > wg ? fwd : wg;
         max_w = sk > max_w ? sk : max_w;
     }
@@ -246,6 +249,8 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
     int frc = layerwise ? -1 : unet_fused_backward(t, p, L, ws, st);
     if (frc > 0) return frc;
     if (frc == 0) {
+        ReduceBatch folds;                               // one launch folds every layer's per-CTA partials at the end
+        size_t poff = 0;
         for (int i = L.unet.nops - 1; i >= 0; --i) {
             const Op& op = L.unet.ops[i];
             int rc = 0;
@@ -253,7 +258,8 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
                 View v = view_of(L, ws, op.in, false);
                 rc = conv1x1_backward(v.p, v.bs, op.in.C, p->conv[op.layer].w, ws + L.d_logits, (long)d.n * d.HW,
                                       op.relu ? ws + L.logits : nullptr, (long)d.n * d.HW, d.n, d.H, L.N, nullptr, 0,
-                                      g->conv[op.layer].w, g->conv[op.layer].b, partials, st);
+                                      g->conv[op.layer].w, g->conv[op.layer].b, partials + poff, st, &folds);
+                poff += align64((size_t)592 * (kMaxObjs * 17));
             } else if (op.kind == OP_CONV) {
                 View o = view_of(L, ws, op.out, false), go = view_of(L, ws, op.out, true);
                 WgradArgs w;
@@ -266,12 +272,14 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
                 w.Cin = op.in.C;
                 w.g = go.p; w.g_bs = go.bs; w.Cout = op.out.C;       // already gated by the layer's ReLU
                 w.act = nullptr;
-                w.S = o.S; w.N = L.N; w.partials = partials;
+                w.S = o.S; w.N = L.N; w.partials = partials + poff;
+                w.defer = &folds;
+                poff += align64(wgrad_partials_floats(op.in.C, op.out.C));
                 rc = conv3x3_wgrad(w, g->conv[op.layer].w, g->conv[op.layer].b, st);
             }
             if (rc) return rc;
         }
-        return 0;
+        return reduce_partials_batch(folds, st);
     }
     for (int i = L.unet.nops - 1; i >= 0; --i) {
         const Op& op = L.unet.ops[i];

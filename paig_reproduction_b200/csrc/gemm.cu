@@ -6,6 +6,7 @@
 #include "internal.h"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace paig {
 
@@ -16,7 +17,11 @@ namespace paig {
 // (16-byte global loads along k, transposed on the way into shared memory) or along m / n (straight vector copy).
 constexpr int kBK = 16, kGemmThreads = 256;
 constexpr int kSplitTargetCtas = 296;     // 2 resident CTAs per SM
-constexpr int kSplitFixedK = 512;         // SPLIT_FIXED chunk length (multiple of kBK)
+static int split_fixed_k() {               // SPLIT_FIXED chunk length (multiple of kBK)
+    static const int v = getenv("PAIG_GEMM_SPLITK") ? atoi(getenv("PAIG_GEMM_SPLITK")) : 512;
+    return v;
+}
+#define kSplitFixedK split_fixed_k()
 
 // four consecutive-k (KFAST) or consecutive-mn elements of an operand, zero outside the matrix
 template <bool KFAST>
@@ -67,7 +72,7 @@ __device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, float v, int m
 }
 
 template <bool A_KFAST, bool B_KFAST, int BM, int BN>
-__global__ void __launch_bounds__(kGemmThreads, 2) sgemm_kernel(GemmArgs g) {
+__global__ void __launch_bounds__(kGemmThreads, (BM == 128 ? 1 : 2)) sgemm_kernel(GemmArgs g) {
     constexpr int TM = BM / 16, TN = BN / 16;          // rows / columns per thread: 4 or 8
     constexpr int LDA = BM + 4, LDB = BN + 4;
     constexpr int A_IT = BM * kBK / 4 / kGemmThreads;   // float4 per thread per slab: 1 or 2
@@ -184,8 +189,11 @@ int gemm(const GemmArgs& in, cudaStream_t st) {
     // 16-byte loads need an aligned base and a leading stride that keeps every vector aligned
     g.a_vec = ((uintptr_t)g.A % 16 == 0) && ((ak ? g.sam : g.sak) % 4 == 0);
     g.b_vec = ((uintptr_t)g.B % 16 == 0) && ((bk ? g.sbn : g.sbk) % 4 == 0);
-    // big tiles (8x8 per thread) when they alone give every SM a CTA, else 64x64 tiles (4x4 per thread)
-    const bool big = g.N > 64 && g.M > 64 && cdiv(g.M, 128) * cdiv(g.N, 128) >= 148;
+    // 64x64 tiles (4x4 per thread, two CTAs per SM) measured faster than 128x128 (8x8 per thread) on every GEMM of the
+    // step (B200: l1 dgrad 0.089 vs 0.111 ms); the big tile stays selectable for experiments (PAIG_GEMM_BIG=1)
+    static const int force_big = getenv("PAIG_GEMM_BIG") ? atoi(getenv("PAIG_GEMM_BIG")) : -1;
+    bool big = false;
+    if (force_big >= 0 && g.N > 64 && g.M > 64) big = force_big != 0;
     const int BM = big ? 128 : 64, BN = big ? 128 : 64;
     const int tiles = cdiv(g.M, BM) * cdiv(g.N, BN);
     int splits = 1;

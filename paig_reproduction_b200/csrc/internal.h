@@ -52,6 +52,23 @@ struct ConvArgs {
 };
 int conv3x3(const ConvArgs& a, cudaStream_t st);
 constexpr int kWgradMaxCtas = 296;
+// Deferred fixed-order reductions of per-CTA partials: the weight-gradient kernels of a whole backward pass queue
+// their (partials -> dW, db) folds here and one launch performs them all.
+struct ReduceBatch {
+    static constexpr int kMax = 24;
+    int n = 0;
+    const float* partials[kMax];
+    int nparts[kMax], stride[kMax], n0[kMax], n1[kMax];
+    float* out0[kMax];
+    float* out1[kMax];
+    bool add(const float* p, int np, int st, int a, float* o0, int b, float* o1) {
+        if (n >= kMax) return false;
+        partials[n] = p; nparts[n] = np; stride[n] = st; n0[n] = a; out0[n] = o0; n1[n] = b; out1[n] = o1;
+        ++n;
+        return true;
+    }
+};
+int reduce_partials_batch(const ReduceBatch& b, cudaStream_t st);
 struct WgradArgs {
     const float* in = nullptr; long in_bs = 0; int Cin = 0;       // layer input
     const float* in_mask = nullptr; long in_mask_bs = 0;          // nullable
@@ -59,6 +76,7 @@ struct WgradArgs {
     const float* act = nullptr; long act_bs = 0;                  // nullable: layer output, for the ReLU mask
     int S = 0, N = 0;
     float* partials = nullptr;                                    // >= wgrad_partials_floats(Cin, Cout)
+    ReduceBatch* defer = nullptr;                                 // queue the final fold instead of launching it
     int in_plane = 0, g_plane = 0;                                // filled by conv3x3_wgrad()
 };
 int conv3x3_wgrad(const WgradArgs& a, float* dW, float* db, cudaStream_t st);
@@ -71,7 +89,7 @@ int conv1x1_forward(const float* in, long in_bs, int Cin, const float* w, const 
                     int Cout, int S, int N, int relu, cudaStream_t st);
 int conv1x1_backward(const float* in, long in_bs, int Cin, const float* w, const float* dout, long dout_bs,
                      const float* act, long act_bs, int Cout, int S, int N, float* din, long din_bs, float* dW,
-                     float* db, float* partials, cudaStream_t st);
+                     float* db, float* partials, cudaStream_t st, ReduceBatch* defer = nullptr);
 int maxpool2(const float* in, long in_bs, float* out, long out_bs, int C, int So, int N, cudaStream_t st);
 int maxpool2_backward(const float* in, long in_bs, const float* dout, long dout_bs, float* din, long din_bs, int C,
                       int So, int N, cudaStream_t st);

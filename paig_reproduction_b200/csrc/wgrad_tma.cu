@@ -314,6 +314,7 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
     int rc = check_launch("conv3x3_wgrad");
     if (rc) return rc;
     const int nW = a.Cout * a.Cin * 9;
+    if (w.defer) return w.defer->add(a.partials, ctas, nW + a.Cout, nW, dW, a.Cout, db) ? 0 : 1;
     return reduce_partials(a.partials, ctas, nW + a.Cout, nW, dW, a.Cout, db, st);
 }
 
