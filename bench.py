@@ -127,6 +127,7 @@ def main():
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")         # keep stdout to the one JSON line
     import torch
     import torch.distributed as dist
 
@@ -245,7 +246,8 @@ def main():
                  (16, 16, 16), (16, 16, 32), (24, 8, 32), (8, 8, 32)]
         f_fwd = sum(2.0 * 9 * ci * co * s * s for ci, co, s in convs) * N
         f_dgrad = sum(2.0 * 9 * ci * co * s * s for ci, co, s in convs[1:]) * N       # no input gradient for c1
-        flops = {"conv3x3": f_fwd + f_dgrad, "conv3x3_wgrad": f_fwd,
+        # fused kernels (unet_fused.cu) or, under PAIG_UNET_LAYERWISE=1, the per-layer conv3x3 kernel
+        flops = {"unet_fused_fwd": f_fwd, "unet_fused_bwd": f_dgrad, "conv3x3": f_fwd + f_dgrad, "conv3x3_wgrad": f_fwd,
                  "sgemm": 2.0 * 3 * (2 * N) * (3072 * 200 + 200 * 200 + 200 * 2)}
         # the MLP GEMMs are profiled under several names (sgemm, sgemm_l1_fwd, ...): one group for the roofline
         sg = [k for k in kern if k.startswith("sgemm")]
@@ -259,6 +261,7 @@ def main():
             ach = flops[top] / (kern[top]["ms_per_step"] * 1e-3) / 1e12
             traffic = None
             try:
+                # DRAM bytes (read + write) of this kernel group per step, from the committed `ncu --set full` capture
                 traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_traffic.json"))).get(top)
             except (OSError, ValueError):
                 pass
@@ -274,8 +277,8 @@ def main():
                 "config": {"workload": "spring_color PhysicsNet LIVE training step (fwd+bwd, all parameter gradients), "
                                        "2 objects, 32x32 RGB, T=12, batch 100 per GPU", "task": TASK, "batch_per_gpu": B_PER_GPU,
                            "global_batch": seqs, "parallelism": "dp%d" % world, "alpha": ALPHA,
-                           "l2": "inputs rotate over a %d x 14.7 MB pool (> 126 MB L2); the 1 GB activation workspace streams "
-                                 "through L2 every step" % POOL,
+                           "l2": "inputs rotate over a %d x 14.7 MB pool (> 126 MB L2); ~0.8 GB of saved activations and "
+                                 "gradients stream through L2 every step" % POOL,
                            "grad_allreduce": "NCCL sum of one flat fp32 buffer + 16 B fp64" if world > 1 else "none (1 GPU)",
                            "optimizer": "not part of the metric (fwd+bwd, BASELINE.json)"},
                 "clocks": sampler.summary(),

@@ -176,6 +176,22 @@ int paig_conv3x3_forward(const float* x, const float* w, const float* b, float* 
 int paig_conv3x3_backward(const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
                           float* db, int N, int Cin, int Cout, int S, int relu, void* workspace, void* stream);
 
+/* ---- the steps either side of the hot path in the training loop ---------------- */
+
+/* optimizer.step() of base.py:152 over a flat buffer, torch.optim defaults of the base.py:12-17 table.
+ * kind: 0 sgd, 1 momentum (0.9), 2 rmsprop (alpha .99, eps 1e-8), 3 adam (betas .9/.999, eps 1e-8).
+ * state0 / state1: momentum buffer | square average | (exp_avg, exp_avg_sq); zero-initialised by the caller;
+ * unused ones may be NULL.  step: 1-based step count (Adam bias correction, first momentum step). */
+int paig_optimizer_step(int kind, float* params, const float* grads, float* state0, float* state1, long n, float lr,
+                        int step, void* stream);
+int paig_optimizer_step_f64(int kind, double* params, const double* grads, double* state0, double* state1, long n,
+                            double lr, int step, void* stream);
+
+/* get_batch (physics_models.py:113-117, iterators.py:26-40,64) from a device-resident uint8 dataset:
+ * out[b][j] = data[idx[b]][j] / 255 as float32, j < seq_elems (= T*H*W*C; the reference's layout change is a reshape,
+ * SURVEY Q15).  idx: device int64 [B]. */
+int paig_gather_batch_u8(const uint8_t* data, long seq_elems, const long* idx, int B, float* out, void* stream);
+
 /* Measurement hooks (bench.py): cumulative number of kernels this library launched; per-launch CUDA-event
  * timing between begin/end, reported as "kernel-name launches total_ms" lines. */
 long paig_launch_count(void);

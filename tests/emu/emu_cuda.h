@@ -37,6 +37,7 @@ struct dim3 {
 struct float2 { float x, y; };
 struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
 struct int2 { int x, y; };
+struct __attribute__((aligned(4))) uchar4 { unsigned char x, y, z, w; };
 struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
