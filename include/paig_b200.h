@@ -198,6 +198,10 @@ long paig_launch_count(void);
 void paig_profile_begin(void);
 int paig_profile_end(char* buf, size_t cap);
 
+/* Test hook: C[M,N] = A[M,K] . B[N,K]^T on the tcgen05 3xTF32 path (csrc/gemm_tc.cu); scratch holds the split-K partials. */
+int paig_debug_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int fixed_split, float* scratch,
+                       long scratch_floats, void* stream);
+
 /* Test hook: offset (in floats) of a named workspace region ("act", "grad" with a UNet buffer index; "logits",
  * "d_logits", "enc_pos", "d_enc_pos", "seq", "d_seq", "d_consts", "consts", "A", "dA"), or -1. */
 long paig_debug_workspace_offset(const paig_task* t, int B, const char* region, int index);

@@ -225,6 +225,11 @@ int gemm(const GemmArgs& in, cudaStream_t st) {
     return check_launch("splitk_reduce");
 }
 
+int gemm_fold_partials(const GemmArgs& g, int splits, cudaStream_t st) {
+    launch(splitk_reduce_kernel, dim3(cdiv((long)g.M * g.N, 256)), dim3(256), 0, st, g, splits);
+    return check_launch("splitk_reduce");
+}
+
 // out[n] = sum_m X[m*ld + n]   (bias gradients).  One warp per 32 columns, fixed order.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int M, int N, int ld,
                                                      float* __restrict__ out) {

@@ -115,6 +115,12 @@ struct GemmArgs {
 };
 int gemm(const GemmArgs& g, cudaStream_t st);
 int colsum(const float* X, int M, int N, int ld, float* out, cudaStream_t st);
+// fold split-K partials g.splitk_ws[splits][M][N] into g.C with g's bias / epilogue (fixed order)
+int gemm_fold_partials(const GemmArgs& g, int splits, cudaStream_t st);
+// gemm_tc.cu -- 3xTF32 tcgen05 GEMM for K-major operands; see the file header for the return convention
+int gemm_tc_partials(const float* A, const float* B, int M, int N, int K, bool fixed_split, float* partials,
+                     size_t partial_floats, const char* tag, cudaStream_t st);
+int transpose(const float* src, float* dst, int R, int C, cudaStream_t st);
 int linear_forward(const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int epi,
                    cudaStream_t st, float* splitk_ws = nullptr, size_t splitk_floats = 0, const char* tag = nullptr);
 int linear_dgrad(const float* dY, const float* W, float* dX, int M, int K, int N, int epi, const float* aux,

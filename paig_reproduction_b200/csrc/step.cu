@@ -303,6 +303,17 @@ int paig_velocity_backward(const paig_task* t, const paig_params* p, const paig_
     return velocity_backward(t, p, grads, L, ws + L.d_state0, d_enc_pos_accum, ws, st);
 }
 
+int paig_debug_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int fixed_split, float* scratch,
+                       long scratch_floats, void* stream) {
+    const int sp = gemm_tc_partials(A, B, M, N, K, fixed_split != 0, scratch, (size_t)scratch_floats, "gemm_tf32x3",
+                                    (cudaStream_t)stream);
+    if (sp < 0) { set_error("gemm_tc: shape %d x %d x %d does not qualify", M, N, K); return 1; }
+    if (sp == 0) return 2;
+    GemmArgs g;
+    g.C = C; g.ldc = N; g.M = M; g.N = N; g.splitk_ws = scratch;
+    return gemm_fold_partials(g, sp, (cudaStream_t)stream);
+}
+
 long paig_debug_workspace_offset(const paig_task* t, int B, const char* region, int index) {
     if (!valid_task(t) || !region) return -1;
     const Layout L = make_layout(t, B);
