@@ -225,13 +225,14 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
 // ---- host ---------------------------------------------------------------------------------------------------
 namespace {
 
-// smallest multiple of 4 >= need such that rows * boxx == +-4 (mod 32): channel planes land 4 banks apart
+// Smallest box width >= need that keeps 16-byte loads of 8 consecutive lanes (= 8 channel planes) conflict-free:
+// plane = rows * boxx floats must be 4 * odd (mod 32), i.e. rows odd and boxx = 4 * odd -- the planes' first banks
+// are then the 8 distinct multiples of 4.
 int pick_boxx(int need, int rows) {
-    for (int bx = (need + 3) & ~3; bx < need + 40; bx += 4) {
-        const int m = (rows * bx) % 32;
-        if (m == 4 || m == 28) return bx;
-    }
-    return -1;
+    if ((rows & 1) == 0) return -1;
+    int k = (need + 3) / 4;
+    if ((k & 1) == 0) ++k;
+    return 4 * k;
 }
 
 #ifndef PAIG_EMU
