@@ -32,7 +32,7 @@ struct alignas(64) CUtensorMap { unsigned char opaque[128]; };
 namespace paig {
 
 constexpr int kWtThreads = 256;
-constexpr int kWtStages = 2;
+constexpr int kWtMaxStages = 4;
 
 struct TmaView {                 // what the tensor map describes (also drives the emulation path)
     const float* base;           // element (x=0, y=0, c=0, n=0)
@@ -46,6 +46,7 @@ struct WgradTmaArgs {
     int Cin, Cout, S, N, R, strips;
     int in_plane, g_plane;       // boxx * boxy of each view
     int stage_floats, g_off;     // per stage; offset of g inside a stage
+    int stages;                  // 2..4 strips in flight (as many as fit next to the fold buffer)
     float* partials;
 };
 
@@ -82,7 +83,7 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
 #endif
     constexpr int kRed = COB * 10;                                    // floats a thread leaves for the final fold
     PAIG_DYN_SMEM(float, smem_raw);
-    __shared__ unsigned long long full[kWtStages];
+    __shared__ unsigned long long full[kWtMaxStages];
     // TMA tensor destinations must be 128-byte aligned in the shared window; the dynamic segment follows the static
     // barriers, so align explicitly (the launch asks for 128 spare bytes)
 #ifdef PAIG_EMU
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
 #else
     float* smem = smem_raw + (((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u) >> 2);
 #endif
-    const int S = a.S, QX = (S + 3) / 4, R = a.R;
+    const int S = a.S, QX = (S + 3) / 4, R = a.R, kWtStages = a.stages;
     const int tid = threadIdx.x;
     const int cob_n = (a.Cout + COB - 1) / COB;
     const int G = cob_n * a.Cin;                                      // owner groups
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
     const unsigned stage_bytes = (unsigned)((a.Cin * a.in_plane + a.Cout * a.g_plane) * sizeof(float));
 #ifndef PAIG_EMU
     if (tid == 0) {
-        for (int s = 0; s < kWtStages; ++s)
+        for (int s = 0; s < kWtMaxStages; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&full[s])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -299,16 +300,20 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
     const int gsets = cdiv(G, kWtThreads);
     const int G_per = cdiv(G, gsets);
     const int P = kWtThreads / G_per > 0 ? kWtThreads / G_per : 1;
-    const size_t tile = (size_t)kWtStages * a.stage_floats, red = (size_t)P * G_per * COB * 10;
+    const size_t red = (size_t)P * G_per * COB * 10, budget = (110 * 1024 - 128) / sizeof(float);
+    a.stages = (int)(budget / a.stage_floats);
+    if (a.stages > kWtMaxStages) a.stages = kWtMaxStages;
+    if (a.stages < 2) return -1;                                       // two CTAs per SM, two strips in flight
+    const size_t tile = (size_t)a.stages * a.stage_floats;
     const size_t smem = (tile > red ? tile : red) * sizeof(float) + 128;
-    if (smem > 110 * 1024) return -1;                                  // two CTAs per SM
+    if (smem > 110 * 1024) return -1;
     if (!make_map(&a.tm_in, a.vin) || !make_map(&a.tm_g, a.vg)) return -1;
     int ctas = a.N * a.strips;
     if (ctas > kWgradMaxCtas) ctas = kWgradMaxCtas;
     static const bool debug = getenv("PAIG_DEBUG") != nullptr;
     if (debug)
-        fprintf(stderr, "[paig] wgrad_tma %d->%d S=%d N=%d R=%d strips=%d in box %dx%d g box %dx%d stage=%d floats smem=%zu ctas=%d gsets=%d\n",
-                a.Cin, a.Cout, S, a.N, a.R, a.strips, a.vin.boxx, a.vin.boxy, a.vg.boxx, a.vg.boxy, a.stage_floats, smem, ctas,
+        fprintf(stderr, "[paig] wgrad_tma %d->%d S=%d N=%d R=%d strips=%d stages=%d in box %dx%d g box %dx%d stage=%d floats smem=%zu ctas=%d gsets=%d\n",
+                a.Cin, a.Cout, S, a.N, a.R, a.strips, a.stages, a.vin.boxx, a.vin.boxy, a.vg.boxx, a.vg.boxy, a.stage_floats, smem, ctas,
                 gsets);
     if (COB == 8) launch(conv3x3_wgrad_tma_kernel<8>, dim3(ctas, gsets), dim3(kWtThreads), smem, st, a);
     else launch(conv3x3_wgrad_tma_kernel<4>, dim3(ctas, gsets), dim3(kWtThreads), smem, st, a);
