@@ -489,21 +489,32 @@ __device__ __forceinline__ void run_upT(const FusedOp& op, float* sm, int f, int
         up_adj_f(j, Si, wx);
         // output (2i-1, 2j-1) sits at tile (2i, 2j); the halo rows/columns it may touch carry weight 0
         const float* g0 = sm + op.in0 + (2 * i) * go.P + 2 * j;
-        for (int c = sub; c < C; c += nsub) {
-            const float* g = g0 + c * go.plane;
-            float s = 0.f;
+        for (int cb = sub; cb < C; cb += 4 * nsub) {                  // 4 channels per trip: their gate loads overlap
+            float mv[4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                if (wy[a] == 0.f) continue;
-                float r = 0.f;
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if (wx[b] != 0.f) r += wx[b] * g[a * go.P + b];
-                s += wy[a] * r;
+            for (int u = 0; u < 4; ++u) {
+                const int c = cb + u * nsub;
+                mv[u] = (op.gmask && c < C) ? op.gmask[(long)f * op.gmask_bs + ((long)c * Si + i) * Si + j] : 1.f;
             }
-            if (op.gmask && !(op.gmask[(long)f * op.gmask_bs + ((long)c * Si + i) * Si + j] > 0.f)) s = 0.f;
-            if (op.out >= 0) sm[op.out + c * gi.plane + (i + 1) * gi.P + j + 1] = s;
-            if (op.gout) op.gout[(long)f * op.gout_bs + ((long)c * Si + i) * Si + j] = s;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = cb + u * nsub;
+                if (c >= C) continue;
+                const float* g = g0 + c * go.plane;
+                float s = 0.f;
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    if (wy[a] == 0.f) continue;
+                    float r = 0.f;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if (wx[b] != 0.f) r += wx[b] * g[a * go.P + b];
+                    s += wy[a] * r;
+                }
+                if (!(mv[u] > 0.f)) s = 0.f;
+                if (op.out >= 0) sm[op.out + c * gi.plane + (i + 1) * gi.P + j + 1] = s;
+                if (op.gout) op.gout[(long)f * op.gout_bs + ((long)c * Si + i) * Si + j] = s;
+            }
         }
     }
 }
@@ -520,28 +531,42 @@ __device__ __forceinline__ void run_poolT(const FusedOp& op, float* sm, int f, i
     for (int wk = tid; wk < per * nsub; wk += kFusedThreads) {
         const int e = wk % per, sub = wk / per;
         const int y = e / So, x = e % So;
-        for (int c = sub; c < C; c += nsub) {
-            const float* xs = op.gmask + (long)f * op.gmask_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
-            const float2 a = *reinterpret_cast<const float2*>(xs);
-            const float2 b = *reinterpret_cast<const float2*>(xs + Si);
-            const float v[4] = {a.x, a.y, b.x, b.y};
-            int best = 0;
-            float m = v[0];
-            if (v[1] > m) { m = v[1]; best = 1; }
-            if (v[2] > m) { m = v[2]; best = 2; }
-            if (v[3] > m) { m = v[3]; best = 3; }
-            const float g = sm[op.in0 + c * gp.plane + (y + 1) * gp.P + x + 1];
-            const int t00 = c * gx.plane + (2 * y + 1) * gx.P + 2 * x + 1;
-            const int toff[4] = {t00, t00 + 1, t00 + gx.P, t00 + gx.P + 1};
-            const long g00 = (long)f * op.gout_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
-            const long goff[4] = {g00, g00 + 1, g00 + Si, g00 + Si + 1};
+        for (int cb = sub; cb < C; cb += 4 * nsub) {                  // 4 channels per trip: their source loads overlap
+            float2 xa[4], xb[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float r = op.in1 >= 0 ? sm[op.in1 + toff[k]] : 0.f;
-                if (k == best) r += g;
-                if (op.relu && !(v[k] > 0.f)) r = 0.f;
-                if (op.out >= 0) sm[op.out + toff[k]] = r;
-                if (op.gout) op.gout[goff[k]] = r;
+            for (int u = 0; u < 4; ++u) {
+                const int c = cb + u * nsub;
+                if (c < C) {
+                    const float* xs = op.gmask + (long)f * op.gmask_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
+                    xa[u] = *reinterpret_cast<const float2*>(xs);
+                    xb[u] = *reinterpret_cast<const float2*>(xs + Si);
+                } else {
+                    xa[u] = xb[u] = make_float2(0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = cb + u * nsub;
+                if (c >= C) continue;
+                const float v[4] = {xa[u].x, xa[u].y, xb[u].x, xb[u].y};
+                int best = 0;
+                float m = v[0];
+                if (v[1] > m) { m = v[1]; best = 1; }
+                if (v[2] > m) { m = v[2]; best = 2; }
+                if (v[3] > m) { m = v[3]; best = 3; }
+                const float g = sm[op.in0 + c * gp.plane + (y + 1) * gp.P + x + 1];
+                const int t00 = c * gx.plane + (2 * y + 1) * gx.P + 2 * x + 1;
+                const int toff[4] = {t00, t00 + 1, t00 + gx.P, t00 + gx.P + 1};
+                const long g00 = (long)f * op.gout_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
+                const long goff[4] = {g00, g00 + 1, g00 + Si, g00 + Si + 1};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float r = op.in1 >= 0 ? sm[op.in1 + toff[k]] : 0.f;
+                    if (k == best) r += g;
+                    if (op.relu && !(v[k] > 0.f)) r = 0.f;
+                    if (op.out >= 0) sm[op.out + toff[k]] = r;
+                    if (op.gout) op.gout[goff[k]] = r;
+                }
             }
         }
     }
@@ -556,23 +581,34 @@ __device__ __forceinline__ void run_headT(const FusedOp& op, float* sm, int f, i
     if (op.out >= 0) zero_halo_planes(sm + op.out, C, g, tid, kFusedThreads);
     for (int e = tid; e < S * S; e += kFusedThreads) {
         const int y = e / S, x = e % S;
-        float gl[kMaxObjs];
+        float gl[kMaxObjs], hm[kMaxObjs];
+        // global loads first (d logits and the head's own ReLU gate), then the output gates 8 channels at a time
 #pragma unroll
         for (int o = 0; o < kMaxObjs; ++o) {
-            gl[o] = 0.f;
-            if (o < NO) {
-                gl[o] = op.gsrc[(long)f * op.gsrc_bs + (long)o * S * S + e];
-                if (op.gmask2 && !(op.gmask2[(long)f * op.gmask2_bs + (long)o * S * S + e] > 0.f)) gl[o] = 0.f;
-            }
+            gl[o] = o < NO ? op.gsrc[(long)f * op.gsrc_bs + (long)o * S * S + e] : 0.f;
+            hm[o] = (o < NO && op.gmask2) ? op.gmask2[(long)f * op.gmask2_bs + (long)o * S * S + e] : 1.f;
         }
-        for (int c = 0; c < C; ++c) {
-            float d = 0.f;
 #pragma unroll
-            for (int o = 0; o < kMaxObjs; ++o)
-                if (o < NO) d += w[o * C + c] * gl[o];
-            if (op.gmask && !(op.gmask[(long)f * op.gmask_bs + (long)c * S * S + e] > 0.f)) d = 0.f;
-            if (op.out >= 0) sm[op.out + c * g.plane + (y + 1) * g.P + x + 1] = d;
-            if (op.gout) op.gout[(long)f * op.gout_bs + (long)c * S * S + e] = d;
+        for (int o = 0; o < kMaxObjs; ++o)
+            if (!(hm[o] > 0.f)) gl[o] = 0.f;
+        for (int c0 = 0; c0 < C; c0 += 8) {
+            float mk[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                mk[u] = (c0 + u < C && op.gmask) ? op.gmask[(long)f * op.gmask_bs + (long)(c0 + u) * S * S + e] : 1.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int c = c0 + u;
+                if (c < C) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int o = 0; o < kMaxObjs; ++o)
+                        if (o < NO) d += w[o * C + c] * gl[o];
+                    if (!(mk[u] > 0.f)) d = 0.f;
+                    if (op.out >= 0) sm[op.out + c * g.plane + (y + 1) * g.P + x + 1] = d;
+                    if (op.gout) op.gout[(long)f * op.gout_bs + (long)c * S * S + e] = d;
+                }
+            }
         }
     }
 }
@@ -604,20 +640,28 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_bwd_kernel(const 
             const FusedOp& o = s_ops[P.first_w];
             bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
         }
+#ifndef PAIG_EMU
+        if (P.timing && tid == 0 && f == blockIdx.x + gridDim.x) P.timing[(long)blockIdx.x * 160] = clock64();
+#endif
         for (int t = 0; t < P.nops; ++t) {
             const FusedOp op = s_ops[t];
             if (tid == 0 && op.next_w >= 0) {
                 const FusedOp& o = s_ops[op.next_w];
                 bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
             }
+            long long* tm = nullptr;
+#ifndef PAIG_EMU
+            if (P.timing && tid == 0 && f == blockIdx.x + gridDim.x) tm = P.timing + (long)blockIdx.x * 160 + 32 + t * 4;
+#endif
             if (op.wfloats) {
                 if (op.wbar == 0) { bulk_wait(&bars[0], phase0); phase0 ^= 1u; }
                 else { bulk_wait(&bars[1], phase1); phase1 ^= 1u; }
             }
+            PAIG_STAMP(tm, 0);
             if (op.kind == F_CONV) {
-                if (op.Cout == 8) run_conv_co<8>(op, sm, f, tid, nullptr);
-                else if (op.Cout == 16) run_conv_co<16>(op, sm, f, tid, nullptr);
-                else run_conv_co<32>(op, sm, f, tid, nullptr);
+                if (op.Cout == 8) run_conv_co<8>(op, sm, f, tid, tm);
+                else if (op.Cout == 16) run_conv_co<16>(op, sm, f, tid, tm);
+                else run_conv_co<32>(op, sm, f, tid, tm);
             } else if (op.kind == F_UPT) {
                 run_upT(op, sm, f, tid);
             } else if (op.kind == F_POOLT) {
@@ -626,6 +670,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_bwd_kernel(const 
                 run_headT(op, sm, f, tid);
             }
             __syncthreads();
+#ifndef PAIG_EMU
+            if (P.timing && tid == 0 && f == blockIdx.x + gridDim.x) P.timing[(long)blockIdx.x * 160 + 1 + t] = clock64();
+#endif
         }
     }
 }
@@ -783,6 +830,40 @@ size_t unet_wpack_floats(const UNetDesc& u, const paig_task* t) {
     }
     return 2 * total;
 }
+
+#ifndef PAIG_EMU
+// PAIG_DEBUG: cycles per op (second frame of every CTA, mean over CTAs) and thread 0's phases inside each conv
+static long long* g_timing_buf = nullptr;
+static long long* timing_buffer() {
+    if (!g_timing_buf) cudaMalloc(&g_timing_buf, (size_t)160 * 160 * sizeof(long long));
+    return g_timing_buf;
+}
+static void print_timing(const char* what, const FusedPlan& P, int grid, int N, cudaStream_t st) {
+    if (N < 2 * grid) return;
+    cudaStreamSynchronize(st);
+    static long long host[160 * 160];
+    cudaMemcpy(host, g_timing_buf, (size_t)grid * 160 * sizeof(long long), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[paig] %s cycles per op (mean over %d CTAs):", what, grid);
+    double total = 0;
+    for (int k = 0; k < P.nops; ++k) {
+        double s = 0;
+        for (int b = 0; b < grid; ++b) s += (double)(host[b * 160 + 1 + k] - host[b * 160 + k]);
+        fprintf(stderr, " op%d=%.0f", k, s / grid);
+        total += s / grid;
+    }
+    fprintf(stderr, " total=%.0f\n", total);
+    fprintf(stderr, "[paig]   thread 0 of CTA 0: op: wait | halo | compute | epilogue | sync\n");
+    for (int k = 0; k < P.nops; ++k) {
+        const long long* tmh = host + 32 + k * 4;
+        if (P.ops[k].kind == F_CONV && P.ops[k].up)
+            fprintf(stderr, "[paig]   op%-2d (up) wait %lld | halo %lld | upsample total %lld | accumulate total %lld\n", k,
+                    tmh[0] - host[k], tmh[1] - tmh[0], tmh[2], tmh[3]);
+        if (P.ops[k].kind == F_CONV && !P.ops[k].up)
+            fprintf(stderr, "[paig]   op%-2d %6lld | %6lld | %6lld | %6lld | %6lld\n", k, tmh[0] - host[k], tmh[1] - tmh[0],
+                    tmh[2] - tmh[1], tmh[3] - tmh[2], host[1 + k] - tmh[3]);
+    }
+}
+#endif
 
 // Returns 0 on success, 1 on error, -1 when the network does not fit on chip (caller uses the per-layer path).
 int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride, int fps,
@@ -956,38 +1037,13 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
         if (rc) return rc;
         int grid = L.N < sm_count() ? L.N : sm_count();
 #ifndef PAIG_EMU
-        static long long* timing_buf = nullptr;
-        if (debug && !timing_buf) cudaMalloc(&timing_buf, (size_t)sm_count() * 160 * sizeof(long long));
-        P.timing = debug ? timing_buf : nullptr;
+        P.timing = debug ? timing_buffer() : nullptr;
 #endif
         launch(unet_fused_fwd_kernel, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
         (void)t;
         rc = check_launch("unet_fused_fwd");
 #ifndef PAIG_EMU
-        if (debug && !rc && L.N >= 2 * grid) {          // cycles per op, second frame of every CTA, mean over CTAs
-            cudaStreamSynchronize(st);
-            static long long host[160 * 160];
-            cudaMemcpy(host, timing_buf, (size_t)grid * 160 * sizeof(long long), cudaMemcpyDeviceToHost);
-            fprintf(stderr, "[paig] fused UNet cycles per op (mean over %d CTAs):", grid);
-            double total = 0;
-            for (int k = 0; k < nf; ++k) {
-                double s = 0;
-                for (int b = 0; b < grid; ++b) s += (double)(host[b * 160 + 1 + k] - host[b * 160 + k]);
-                fprintf(stderr, " op%d=%.0f", k, s / grid);
-                total += s / grid;
-            }
-            fprintf(stderr, " total=%.0f\n", total);
-            fprintf(stderr, "[paig]   thread 0 of CTA 0: op: wait | halo | compute | epilogue | sync\n");
-            for (int k = 0; k < nf; ++k) {
-                const long long* tmh = host + 32 + k * 4;
-                if (P.ops[k].kind == F_CONV && P.ops[k].up)
-                    fprintf(stderr, "[paig]   op%-2d (up) wait %lld | halo %lld | upsample total %lld | accumulate total %lld\n", k,
-                            tmh[0] - host[k], tmh[1] - tmh[0], tmh[2], tmh[3]);
-                if (P.ops[k].kind == F_CONV && !P.ops[k].up)
-                    fprintf(stderr, "[paig]   op%-2d %6lld | %6lld | %6lld | %6lld | %6lld\n", k, tmh[0] - host[k], tmh[1] - tmh[0],
-                            tmh[2] - tmh[1], tmh[3] - tmh[2], host[1 + k] - tmh[3]);
-            }
-        }
+        if (debug && !rc) print_timing("fused UNet forward", P, grid, L.N, st);
 #endif
         return rc;
     }
@@ -1224,9 +1280,16 @@ int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& 
     int rc = check_launch("pack_weights");
     if (rc) return rc;
     const int grid = L.N < sm_count() ? L.N : sm_count();
+#ifndef PAIG_EMU
+    P.timing = debug ? timing_buffer() : nullptr;
+#endif
     launch(unet_fused_bwd_kernel, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
     (void)t;
-    return check_launch("unet_fused_bwd");
+    rc = check_launch("unet_fused_bwd");
+#ifndef PAIG_EMU
+    if (debug && !rc) print_timing("fused UNet backward-data", P, grid, L.N, st);
+#endif
+    return rc;
 }
 
 }  // namespace paig
