@@ -305,6 +305,16 @@ __device__ __forceinline__ void run_conv(const FusedOp& op, float* sm, int f, in
                 for (int c = 0; c < CO; ++c)
 #pragma unroll
                     for (int p = 0; p < 4; ++p) acc[r][c][p] = 0.f;
+#ifndef PAIG_EMU
+            if (op.gmask) {                  // the epilogue's ReLU gates live in HBM: pull their lines into L2 while we compute
+#pragma unroll
+                for (int r = 0; r < PY; ++r)
+#pragma unroll
+                    for (int c = 0; c < CO; ++c)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(op.gmask + (long)f * op.gmask_bs +
+                                                                       ((long)(cg * CO + c) * op.S + y + r) * op.S + 4 * qx));
+            }
+#endif
             conv_accumulate<CO, COUT, PY>(acc, sm + op.in0, op.Cin0, g, w + cg * CO, y, qx);
             if (op.Cin1)
                 conv_accumulate<CO, COUT, PY>(acc, sm + op.in1, op.Cin1, g, w + op.Cin0 * 9 * COUT + cg * CO, y, qx);
