@@ -530,14 +530,16 @@ __global__ void __launch_bounds__(256) conv1x1_bwd_kernel(const float* __restric
         for (int c = 0; c < kMaxHeadIn; ++c) {
             if (c < Cin) {
                 const float v = in[(long)f * in_bs + (long)c * HW + p];
-                float d = 0.f;
 #pragma unroll
                 for (int o = 0; o < kMaxObjs; ++o)
-                    if (o < Cout) {
-                        aw[o][c] += g[o] * v;
-                        d += w[o * Cin + c] * g[o];
-                    }
-                if (din) din[(long)f * din_bs + (long)c * HW + p] = d;
+                    if (o < Cout) aw[o][c] += g[o] * v;
+                if (din) {                       // (the fused backward-data kernel computes d in itself: din == NULL)
+                    float d = 0.f;
+#pragma unroll
+                    for (int o = 0; o < kMaxObjs; ++o)
+                        if (o < Cout) d += w[o * Cin + c] * g[o];
+                    din[(long)f * din_bs + (long)c * HW + p] = d;
+                }
             }
         }
     }
