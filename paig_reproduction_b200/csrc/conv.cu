@@ -474,6 +474,24 @@ int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t s
     return reduce_partials(a.partials, ctas, nW + a.Cout, nW, dW, a.Cout, db, st);
 }
 
+// g *= (act > 0) in place over channel-sliced NCHW views: the ReLU adjoint applied once, so that the weight-gradient
+// kernel can take g through TMA (wgrad_tma.cu needs an already gated gradient) and the data-gradient kernel's own
+// gate becomes a no-op.
+__global__ void __launch_bounds__(256) relu_gate_kernel(float* __restrict__ g, long g_bs, const float* __restrict__ act,
+                                                        long act_bs, long per_frame, long total) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long f = idx / per_frame, r = idx % per_frame;
+    if (!(act[f * act_bs + r] > 0.f)) g[f * g_bs + r] = 0.f;
+}
+
+int relu_gate(float* g, long g_bs, const float* act, long act_bs, int C, int S, int N, cudaStream_t st) {
+    const long per = (long)C * S * S, total = per * N;
+    if (total <= 0) return 0;
+    launch(relu_gate_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, g, g_bs, act, act_bs, per, total);
+    return check_launch("relu_gate");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // 1x1 head (blocks.py:236,307): Cin in {8,16} -> Cout = n_objs.  One thread per pixel.
 // ---------------------------------------------------------------------------------------------------------

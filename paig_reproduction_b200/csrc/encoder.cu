@@ -301,7 +301,10 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
             }
             w.Cin = op.in.C;
             w.g = go.p; w.g_bs = go.bs; w.Cout = op.out.C;
-            w.act = op.relu ? o.p : nullptr; w.act_bs = o.bs;
+            // gate the gradient once in place: the TMA weight-gradient kernel needs it pre-gated, and the data-gradient
+            // kernel's own gate below becomes idempotent
+            if (op.relu && (rc = relu_gate(go.p, go.bs, o.p, o.bs, op.out.C, o.S, L.N, st))) return rc;
+            w.act = nullptr;
             w.S = o.S; w.N = L.N; w.partials = partials;
             rc = conv3x3_wgrad(w, g->conv[op.layer].w, g->conv[op.layer].b, st);
             if (!rc && op.in.buf >= 0) {        // no gradient w.r.t. the input frames

@@ -85,6 +85,7 @@ int conv3x3_wgrad_tma(const WgradArgs& a, float* dW, float* db, cudaStream_t st)
 size_t wgrad_partials_floats(int Cin, int Cout);
 int reduce_partials(const float* partials, int nparts, int stride, int n0, float* out0, int n1, float* out1,
                     cudaStream_t st);
+int relu_gate(float* g, long g_bs, const float* act, long act_bs, int C, int S, int N, cudaStream_t st);
 int conv1x1_forward(const float* in, long in_bs, int Cin, const float* w, const float* b, float* out, long out_bs,
                     int Cout, int S, int N, int relu, cudaStream_t st);
 int conv1x1_backward(const float* in, long in_bs, int Cin, const float* w, const float* dout, long dout_bs,
