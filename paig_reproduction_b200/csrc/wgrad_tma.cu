@@ -285,25 +285,45 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
     WgradTmaArgs a;
     memset(&a, 0, sizeof(a));
     a.Cin = w.Cin; a.Cout = w.Cout; a.S = S; a.N = w.N; a.partials = w.partials;
-    a.R = S >= 14 ? 7 : ((S + 1) | 1);                                 // odd strip heights keep R and R+2 odd
-    a.strips = cdiv(S, a.R);
-    a.vin = TmaView{w.in, S, w.Cin, w.N, w.in_bs, pick_boxx(S + 5, a.R + 2), a.R + 2};    // image columns -4 .. S
-    a.vg = TmaView{w.g, S, w.Cout, w.N, w.g_bs, pick_boxx(S, a.R), a.R};
-    if (a.vin.boxx < 0 || a.vg.boxx < 0 || a.vin.boxx > 256 || a.vg.boxx > 256) return -1;
-    a.in_plane = a.vin.boxx * a.vin.boxy;
-    a.g_plane = a.vg.boxx * a.vg.boxy;
-    a.g_off = (a.Cin * a.in_plane + 31) & ~31;                         // 128-byte aligned TMA destinations
-    a.stage_floats = (a.g_off + a.Cout * a.g_plane + 31) & ~31;
+    // Strip height: odd (so R and R+2 are odd, pick_boxx); the tallest of {whole image, 13, 11, 9, 7, 5, 3} that
+    // still leaves two strips in flight per CTA and wastes the fewest rows -- fewer, fuller strips per frame mean
+    // fewer barrier round trips and less halo re-read.
+    static const int forced_R = getenv("PAIG_WGRAD_R") ? atoi(getenv("PAIG_WGRAD_R")) : 0;
+    const size_t budget = (110 * 1024 - 128) / sizeof(float);
+    const int cands[7] = {(S + 1) | 1, 13, 11, 9, 7, 5, 3};
+    bool found = false;
+    double best_cost = 0;
+    WgradTmaArgs best = a;
+    for (int ci = 0; ci < 7; ++ci) {
+        const int R = forced_R > 0 ? forced_R : cands[ci];
+        if (R > ((S + 1) | 1) || (R & 1) == 0) continue;
+        WgradTmaArgs c = a;
+        c.R = R;
+        c.strips = cdiv(S, R);
+        c.vin = TmaView{w.in, S, w.Cin, w.N, w.in_bs, pick_boxx(S + 5, R + 2), R + 2};    // image columns -4 .. S
+        c.vg = TmaView{w.g, S, w.Cout, w.N, w.g_bs, pick_boxx(S, R), R};
+        if (c.vin.boxx < 0 || c.vg.boxx < 0 || c.vin.boxx > 256 || c.vg.boxx > 256 || R + 2 > 256) continue;
+        c.in_plane = c.vin.boxx * c.vin.boxy;
+        c.g_plane = c.vg.boxx * c.vg.boxy;
+        c.g_off = (c.Cin * c.in_plane + 31) & ~31;                     // 128-byte aligned TMA destinations
+        c.stage_floats = (c.g_off + c.Cout * c.g_plane + 31) & ~31;
+        c.stages = (int)(budget / c.stage_floats);
+        if (c.stages > kWtMaxStages) c.stages = kWtMaxStages;
+        if (c.stages < 2) continue;                                    // two CTAs per SM, two strips in flight
+        // rows fetched per frame (halo re-reads + padding of the last strip) plus a fixed cost per strip
+        const double cost = (double)c.strips * (R + 2) + 3.0 * c.strips;
+        if (!found || cost < best_cost) { found = true; best_cost = cost; best = c; }
+        if (forced_R > 0) break;
+    }
+    if (!found) return -1;
+    a = best;
     const int COB = (a.Cout % 8) == 0 ? 8 : 4;
     if (a.Cout % COB) return -1;
     const int G = ((a.Cout + COB - 1) / COB) * a.Cin;
     const int gsets = cdiv(G, kWtThreads);
     const int G_per = cdiv(G, gsets);
     const int P = kWtThreads / G_per > 0 ? kWtThreads / G_per : 1;
-    const size_t red = (size_t)P * G_per * COB * 10, budget = (110 * 1024 - 128) / sizeof(float);
-    a.stages = (int)(budget / a.stage_floats);
-    if (a.stages > kWtMaxStages) a.stages = kWtMaxStages;
-    if (a.stages < 2) return -1;                                       // two CTAs per SM, two strips in flight
+    const size_t red = (size_t)P * G_per * COB * 10;
     const size_t tile = (size_t)a.stages * a.stage_floats;
     const size_t smem = (tile > red ? tile : red) * sizeof(float) + 128;
     if (smem > 110 * 1024) return -1;

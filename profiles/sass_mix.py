@@ -12,6 +12,7 @@ def opc(s):
     return (t[1] if t[0].startswith("@") else t[0]).split(".")[0]
 tot = 0; byop = collections.Counter(); samp = collections.Counter(); allsamp = 0
 for r in data:
+    if len(r) <= max(iS, iE, iSm): continue
     try: n = int(r[iE])
     except ValueError: continue
     byop[opc(r[iS])] += n; tot += n
@@ -22,6 +23,7 @@ for k, v in byop.most_common(14):
     print("%-10s %12d %5.1f%%   samples %5.1f%%" % (k, v, 100.0 * v / tot, 100.0 * samp[k] / max(allsamp, 1)))
 blocks, cur, last = [], [], None
 for i, r in enumerate(data):
+    if len(r) <= max(iS, iE, iSm): continue
     try: n = int(r[iE])
     except ValueError: n = 0
     if last is not None and n != last and cur:

@@ -146,3 +146,52 @@ def test_eval_batch_sweep_properties():
         small = net(x[100:103])
         assert torch.equal(net.pos_vel_seq, pv_big[100:103])
         assert torch.equal(small, big[100:103])
+
+
+def _grads_of_step(net, x):
+    net.train_step(x)
+    torch.cuda.synchronize()
+    return {k: p.grad.detach().double().clone() for k, p in net.named_parameters() if p.grad is not None}
+
+
+def test_full_batch_loss_weight_linearity():
+    """Size-independent property at BASELINE's batch (100): train = pred + alpha * recons, so every parameter gradient
+    is affine in alpha: g(3) - g(0) == 3 * (g(1) - g(0)).  Exercises the in-kernel loss gradient of the fused step."""
+    spec = po.TASKS["spring_color"]
+    x = po.synthetic_frames(spec, 100, spec.seq_len, 11).to(DEV)
+    sd = po.init_state_dict(spec, 0)
+    g = {}
+    for alpha in (0.0, 1.0, 3.0):
+        net = _net("spring_color", spec.seq_len, alpha)
+        net.load_state_dict(sd, strict=True)
+        g[alpha] = _grads_of_step(net, x)
+    # alpha = 0 leaves the reconstruction-only parameters without a gradient path through recons; compare the common keys
+    for k in g[3.0]:
+        if k not in g[0.0] or k not in g[1.0]:
+            continue
+        lhs, rhs = g[3.0][k] - g[0.0][k], 3.0 * (g[1.0][k] - g[0.0][k])
+        scale = max(g[3.0][k].abs().max().item(), 1e-30)
+        assert (lhs - rhs).abs().max().item() <= 2e-4 * scale, k
+
+
+def test_two_shards_sum_to_the_full_batch_gradient():
+    """The data-parallel contract on one GPU: two shards of 50 with batch_global = 100 reproduce the batch-100 step."""
+    spec = po.TASKS["spring_color"]
+    x = po.synthetic_frames(spec, 100, spec.seq_len, 12).to(DEV)
+    sd = po.init_state_dict(spec, 0)
+    full = _net("spring_color", spec.seq_len, 3.0)
+    full.load_state_dict(sd, strict=True)
+    want = _grads_of_step(full, x)
+    want_losses = full._loss_view.detach().double().clone()
+    acc, losses = None, 0.0
+    for lo, hi in ((0, 50), (50, 100)):
+        net = _net("spring_color", spec.seq_len, 3.0)
+        net.load_state_dict(sd, strict=True)
+        net.batch_global = 100
+        got = _grads_of_step(net, x[lo:hi])
+        losses = losses + net._loss_view.detach().double()
+        acc = got if acc is None else {k: acc[k] + got[k] for k in got}
+    assert torch.allclose(losses, want_losses, rtol=1e-5)
+    for k in want:
+        scale = max(want[k].abs().max().item(), 1e-30)
+        assert (acc[k] - want[k]).abs().max().item() <= 2e-4 * scale, k
