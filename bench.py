@@ -197,20 +197,30 @@ def main():
     P, G = net._param_table(params), net._param_table(net._grad_views)
     losses_host = torch.empty(4).pin_memory()
 
+    copy_stream = torch.cuda.Stream(dev)
+
+    def stage(i):                                 # H2D of batch i into slot i % 2 on the copy stream
+        _lib.check(lib.paig_stage_input_host(ctypes.byref(tk), host_pool[i % POOL].data_ptr(), B_PER_GPU, i % 2, ws.data_ptr(),
+                                             copy_stream.cuda_stream))
+
     def step_host(i):
-        _lib.check(lib.paig_step_fused_host(ctypes.byref(tk), ctypes.byref(P), ctypes.byref(G), host_pool[i % POOL].data_ptr(),
-                                            B_PER_GPU, losses_host.data_ptr(), ws.data_ptr(), stream.cuda_stream))
+        # every step: its own input comes from pinned host memory (staged one step ahead so the copy hides under the
+        # previous step's kernels), the four losses go back to the host and are read before the next step starts
+        stage(i + 1)
+        _lib.check(lib.paig_step_fused_staged(ctypes.byref(tk), ctypes.byref(P), ctypes.byref(G), B_PER_GPU, i % 2,
+                                              losses_host.data_ptr(), ws.data_ptr(), stream.cuda_stream))
         if world > 1:
             allreduce_step(flat, net._phys_grad)
         stream.synchronize()                      # the caller reads the losses every step
         return float(losses_host[0])
 
+    stage(0)
     for i in range(3):
         step_host(i)
     barrier()
     t0 = time.perf_counter()
     e0.record(stream)
-    for i in range(args.steps):
+    for i in range(3, 3 + args.steps):            # the batch counter runs on: slot (i % 2) holds batch i
         step_host(i)
     e1.record(stream)
     barrier()
@@ -284,7 +294,7 @@ def main():
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_val, "unit": "sequences/s", "h2d_bytes_per_step": B_PER_GPU * T * 3 * H * H * 4,
                         "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps,
-                        "api": "paig_step_fused_host (pinned host input, losses read back every step)"},
+                        "api": "paig_stage_input_host + paig_step_fused_staged (pinned host input of every step copied on a side stream one step ahead, losses read back every step)"},
                 "gpu_launches": int(launches),
                 "gpu_launches_per_step": launches / args.steps,
                 "roofline": roof,

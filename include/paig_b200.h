@@ -110,6 +110,15 @@ int paig_step_fused(const paig_task* t, const paig_params* p, const paig_params*
 int paig_step_fused_host(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x_host,
                          int B, float* losses_host, void* workspace, void* stream);
 
+/* The same end-to-end step with the input copy pipelined: paig_stage_input_host enqueues the host->device copy of a
+ * batch into staging slot 0 or 1 of the workspace on `copy_stream` (and records an event); paig_step_fused_staged makes
+ * `stream` wait for that slot and runs the fused step on it, copying the four losses to losses_host (nullable).  A
+ * training loop stages batch k+1 into the other slot right before it launches step k: the copy hides under the step.
+ * The caller must not re-stage a slot before the step that reads it has finished. */
+int paig_stage_input_host(const paig_task* t, const float* x_host, int B, int slot, void* workspace, void* copy_stream);
+int paig_step_fused_staged(const paig_task* t, const paig_params* p, const paig_params* grads, int B, int slot,
+                           float* losses_host, void* workspace, void* stream);
+
 /* ---- stages (also used by the parity tests) ---------------------------------------------------- */
 
 /* cells.py:31-51 / 60-83 / 96-106 iterated `steps` times.  pos_vel_seq: [B, steps+1, 4n]; row 0 must

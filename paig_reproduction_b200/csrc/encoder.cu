@@ -181,6 +181,7 @@ Layout make_layout(const paig_task* t, int B) {
     L.wpack = take(unet_wpack_floats(L.unet, t));
     L.frames = take(N * d.CHW);
     L.x_stage = take((size_t)B * d.T * d.CHW);
+    L.x_stage2 = take((size_t)B * d.T * d.CHW);
     L.total = off;
     return L;
 }

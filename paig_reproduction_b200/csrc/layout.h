@@ -50,7 +50,8 @@ struct Layout {
     size_t tc_scratch;           // transposed operands of the tcgen05 encoder.l1 GEMMs: W1^T | dH1^T | A^T
     size_t wpack;                // UNet weights re-packed [ci][tap][co]|bias for the fused forward kernel
     size_t frames;               // gathered encoder frames [N,3,H,H] (when they are a prefix of each sequence)
-    size_t x_stage;              // device copy of the input for the *_host entry point
+    size_t x_stage;              // device copy of the input for the *_host entry points (slot 0)
+    size_t x_stage2;             // second slot: paig_stage_input_host(slot 1) lands here while a step reads slot 0
     size_t total;
 };
 

@@ -250,6 +250,43 @@ int paig_step_fused_host(const paig_task* t, const paig_params* p, const paig_pa
     return check_launch("step_fused_host");
 }
 
+// ---- pipelined host input: copy batch k+1 on a side stream while step k computes -----------------------------------
+#ifndef PAIG_EMU
+static cudaEvent_t g_stage_ev[2] = {nullptr, nullptr};
+#endif
+
+int paig_stage_input_host(const paig_task* t, const float* x_host, int B, int slot, void* workspace, void* copy_stream) {
+    if (!valid_task(t)) return 1;
+    if (slot != 0 && slot != 1) { set_error("stage_input_host: slot must be 0 or 1"); return 1; }
+    const Layout L = make_layout(t, B);
+    float* ws = (float*)workspace;
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    cudaMemcpyAsync(ws + (slot ? L.x_stage2 : L.x_stage), x_host, (size_t)B * L.d.T * L.d.CHW * sizeof(float),
+                    cudaMemcpyHostToDevice, cs);
+#ifndef PAIG_EMU
+    if (!g_stage_ev[slot]) cudaEventCreateWithFlags(&g_stage_ev[slot], cudaEventDisableTiming);
+    cudaEventRecord(g_stage_ev[slot], cs);
+#endif
+    return check_launch("stage_input_host");
+}
+
+int paig_step_fused_staged(const paig_task* t, const paig_params* p, const paig_params* grads, int B, int slot,
+                           float* losses_host, void* workspace, void* stream) {
+    if (!valid_task(t)) return 1;
+    if (slot != 0 && slot != 1) { set_error("step_fused_staged: slot must be 0 or 1"); return 1; }
+    const Layout L = make_layout(t, B);
+    float* ws = (float*)workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+#ifndef PAIG_EMU
+    if (!g_stage_ev[slot]) { set_error("step_fused_staged: slot %d was never staged", slot); return 1; }
+    cudaStreamWaitEvent(st, g_stage_ev[slot], 0);
+#endif
+    int rc = step_fused(t, p, grads, ws + (slot ? L.x_stage2 : L.x_stage), B, nullptr, ws, st);
+    if (rc) return rc;
+    if (losses_host) cudaMemcpyAsync(losses_host, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    return check_launch("step_fused_staged");
+}
+
 int paig_encoder_forward(const paig_task* t, const paig_params* p, const float* x, long seq_stride, int frames_per_seq,
                          int N, float* enc_pos, float* enc_masks, float* masked_objs, void* workspace, void* stream) {
     if (!valid_task(t)) return 1;

@@ -195,3 +195,36 @@ def test_two_shards_sum_to_the_full_batch_gradient():
     for k in want:
         scale = max(want[k].abs().max().item(), 1e-30)
         assert (acc[k] - want[k]).abs().max().item() <= 2e-4 * scale, k
+
+
+def test_staged_host_input_step_equals_device_step():
+    """paig_stage_input_host + paig_step_fused_staged (the pipelined end-to-end call bench.py times) computes exactly
+    what paig_step_fused computes on the same batch, for both staging slots."""
+    import ctypes
+    from paig_reproduction_b200 import _lib
+    lib = _lib.load()
+    spec = po.TASKS["spring_color"]
+    B = 6
+    net = _net("spring_color", spec.seq_len, 3.0)
+    net.load_state_dict(po.init_state_dict(spec, 0), strict=True)
+    xs = [po.synthetic_frames(spec, B, spec.seq_len, s).pin_memory() for s in (21, 22)]
+    want = []
+    for x in xs:
+        losses = net.train_step(x.to(DEV)).cpu().clone()
+        want.append((losses, net.flat_gradients().detach().cpu().clone()))
+    tk = net._task(spec.seq_len)
+    ws = net._workspace(spec.seq_len, B, fresh=False)
+    P, G = net._param_table(net._params_now()), net._param_table(net._grad_views)
+    losses_host = torch.empty(4).pin_memory()
+    main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+    for slot, x in enumerate(xs):
+        _lib.check(lib.paig_stage_input_host(ctypes.byref(tk), x.data_ptr(), B, slot, ws.data_ptr(), side.cuda_stream))
+    for slot in (0, 1):
+        _lib.check(lib.paig_step_fused_staged(ctypes.byref(tk), ctypes.byref(P), ctypes.byref(G), B, slot,
+                                              losses_host.data_ptr(), ws.data_ptr(), main.cuda_stream))
+        main.synchronize()
+        assert torch.equal(losses_host, want[slot][0])
+        # gradients agree to rounding: the decoder accumulates template gradients with shared-memory float atomics, whose
+        # order (not value) varies from launch to launch
+        got, ref = net.flat_gradients().detach().cpu()[:-4], want[slot][1][:-4]
+        assert (got - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
