@@ -21,6 +21,8 @@
 #include "common.cuh"
 #include "internal.h"
 
+#include <cstdlib>
+
 namespace paig {
 
 constexpr int kDecThreads = 256;
@@ -46,7 +48,12 @@ __device__ __forceinline__ Tap make_tap(int j, float l, int H, int t) {
     return tp;
 }
 
-template <int NOBJ, bool BWD>
+// GATHER (backward only): instead of scattering every pixel's template / content gradient through shared-memory float
+// atomics (order-dependent, and heavily conflicting: a 2x zoom sends ~16 pixels to each texel), the per-pixel upstream
+// values are parked in shared memory and every texel *gathers* its <= 4 x 4 contributors in two separable passes
+// (along x, then y) in a fixed order: deterministic, and the atomics leave the critical path.  Needs
+// NOBJ*4*(H*H + H*H/2) extra floats; larger frames (64 px) keep the atomic path.
+template <int NOBJ, bool BWD, bool GATHER>
 __global__ void __launch_bounds__(kDecThreads)
 decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB, float* __restrict__ partials) {
     const int t = H / 2, tt = t * t, HW = H * H;
@@ -65,6 +72,9 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
     float* sYw1 = reinterpret_cast<float*>(sY0) + NOBJ * H;
     float* sYw0 = sYw1 + NOBJ * H;
     float* sRed = sYw0 + NOBJ * H;                    // [8 warps][2*NOBJ+1]
+    float* sD = sRed + 8 * (2 * NOBJ + 1);            // GATHER: [NOBJ*4][H][H] per-pixel dL | dC0..2
+    float* sE = sD + (GATHER ? NOBJ * 4 * HW : 0);    // GATHER: [NOBJ*4][H][t] after the x pass
+    float* sInv = sE + (GATHER ? NOBJ * 4 * H * t : 0);   // GATHER: [2 axes][NOBJ][t][8]: first contributor, 6 weights
     __shared__ __align__(8) unsigned long long bar;
 
     stage_bulk(smem, consts, (unsigned)(CN * sizeof(float)), &bar, 0);
@@ -203,6 +213,11 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
                         const int x0 = sX0[o * H + j], y0 = sY0[o * H + i];
                         const float wx1 = sXw1[o * H + j], wx0 = sXw0[o * H + j];
                         const float wy1 = sYw1[o * H + i], wy0 = sYw0[o * H + i];
+                        if (GATHER) {
+                            sD[(o * 4 + 0) * HW + i * H + j] = dL;
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) sD[(o * 4 + 1 + c) * HW + i * H + j] = dC[c];
+                        }
                         float gix = 0.f, giy = 0.f;
 #pragma unroll
                         for (int dy = 0; dy < 2; ++dy) {
@@ -215,11 +230,11 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
                                     const int a = y * t + x;
                                     // value-weighted upstream of this tap over the 1 mask + 3 content channels
                                     float vg = sT5[o * tt + a] * dL;
-                                    atomicAdd(sG + o * tt + a, w * dL);
+                                    if (!GATHER) atomicAdd(sG + o * tt + a, w * dL);
 #pragma unroll
                                     for (int c = 0; c < 3; ++c) {
                                         vg += sSC[(o * 3 + c) * tt + a] * dC[c];
-                                        atomicAdd(sG + NOBJ * tt + (o * 3 + c) * tt + a, w * dC[c]);
+                                        if (!GATHER) atomicAdd(sG + NOBJ * tt + (o * 3 + c) * tt + a, w * dC[c]);
                                     }
                                     // d(bilinear)/d ix = sum_taps value * (+-1 along x) * wy ; same for iy
                                     gix += vg * (dx ? wy : -wy);
@@ -243,6 +258,63 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
             if (lane == 0) sRed[warp * NR + k] = v;
         }
         __syncthreads();
+        if (GATHER && BWD && do_bwd) {
+            // inverse tap tables: texel x of object o hears from columns j with x0(j) == x (weight w0) or x0(j) + 1 == x
+            // (weight w1).  x0 is non-decreasing and grows by one every two columns, so the contributors are <= 6
+            // consecutive columns starting at the first j with x0(j) >= x - 1.
+            for (int e = tid; e < 2 * NOBJ * t; e += kDecThreads) {
+                const int x = e % t, o = (e / t) % NOBJ, axis = e / (t * NOBJ);
+                const int* i0 = (axis ? sY0 : sX0) + o * H;
+                const float* w0 = (axis ? sYw0 : sXw0) + o * H;
+                const float* w1 = (axis ? sYw1 : sXw1) + o * H;
+                int j = 2 * (x - 1 - i0[0]) - 1;                       // analytic guess, then settle on the exact first column
+                j = min(max(j, 0), H - 1);
+                while (j > 0 && i0[j - 1] >= x - 1) --j;
+                while (j < H && i0[j] < x - 1) ++j;
+                float* dst = sInv + (size_t)e * 8;
+                reinterpret_cast<int*>(dst)[0] = j;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int jj = j + k;
+                    float w = 0.f;
+                    if (jj < H) w = i0[jj] == x ? w0[jj] : (i0[jj] + 1 == x ? w1[jj] : 0.f);
+                    dst[1 + k] = w;
+                }
+            }
+            __syncthreads();
+            // x pass: E[oc][i][x] = sum_k w[k] D[oc][i][jlo + k]; a thread keeps one (oc, x) and walks the rows
+            for (int e = tid; e < NOBJ * 4 * t; e += kDecThreads) {
+                const int x = e % t, oc = e / t, o = oc >> 2;
+                const float* inv = sInv + (size_t)(o * t + x) * 8;
+                const int jlo = reinterpret_cast<const int*>(inv)[0];
+                float w[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w[k] = inv[1 + k];
+                const int nk = min(6, H - jlo);
+                for (int i = 0; i < H; ++i) {
+                    const float* row = sD + oc * HW + i * H + jlo;
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        if (k < nk) s += w[k] * row[k];
+                    sE[(oc * H + i) * t + x] = s;
+                }
+            }
+            __syncthreads();
+            // y pass, accumulated into this CTA's gradient block by the texel's only owner
+            for (int e = tid; e < NOBJ * 4 * tt; e += kDecThreads) {
+                const int x = e % t, y = (e / t) % t, oc = e / tt, o = oc >> 2, ch = oc & 3;
+                const float* inv = sInv + (size_t)((NOBJ + o) * t + y) * 8;
+                const int ilo = reinterpret_cast<const int*>(inv)[0];
+                const int nk = min(6, H - ilo);
+                float s = 0.f;
+#pragma unroll
+                for (int k = 0; k < 6; ++k)
+                    if (k < nk) s += inv[1 + k] * sE[(oc * H + ilo + k) * t + x];
+                float* dst = ch == 0 ? sG + o * tt : sG + NOBJ * tt + (o * 3 + ch - 1) * tt;
+                dst[y * t + x] += s;
+            }
+        }
         if (tid < NR) {
             float s = 0.f;
             for (int w = 0; w < kDecThreads / 32; ++w) s += sRed[w * NR + tid];
@@ -270,14 +342,18 @@ __global__ void __launch_bounds__(256) decode_reduce_kernel(const float* __restr
     d_consts[i] = accumulate ? d_consts[i] + s : s;
 }
 
+static int decode_ctas_per_sm() {
+    static const int v = getenv("PAIG_DECODE_CTAS") ? atoi(getenv("PAIG_DECODE_CTAS")) : 2;
+    return v < 1 ? 1 : (v > 5 ? 5 : v);
+}
 int decode_grid(int F) {
-    const int cap = 148 * 2;
+    const int cap = 148 * decode_ctas_per_sm();
     return F < cap ? (F < 1 ? 1 : F) : cap;
 }
 
 size_t decode_partials_floats(const paig_task* t) {
     const Dims d = dims_of(t);
-    return (size_t)(148 * 2) * (size_t)(d.n * d.t * d.t * 4 + 3 * d.HW);
+    return (size_t)(148 * 5) * (size_t)(d.n * d.t * d.t * 4 + 3 * d.HW);
 }
 
 template <int NOBJ>
@@ -289,8 +365,15 @@ static int run_decode(const Dims& d, const float* consts, const DecSeg& a, const
     const int grid = decode_grid(F);
     const size_t tab = (size_t)6 * NOBJ * d.H + 8 * (2 * NOBJ + 1);
     if (bwd) {
-        const size_t smem = ((size_t)2 * CN + tab) * sizeof(float);
-        launch(decode_kernel<NOBJ, true>, dim3(grid), dim3(kDecThreads), smem, st, d.H, consts, a, b, partials);
+        const size_t gather_fl = (size_t)NOBJ * 4 * (d.HW + d.H * d.t) + (size_t)2 * NOBJ * d.t * 8;
+        const size_t smem_g = ((size_t)2 * CN + tab + gather_fl) * sizeof(float);
+        static const bool atomics = getenv("PAIG_DECODE_ATOMICS") != nullptr;
+        if (!atomics && smem_g <= 110 * 1024) {             // two CTAs per SM
+            launch(decode_kernel<NOBJ, true, true>, dim3(grid), dim3(kDecThreads), smem_g, st, d.H, consts, a, b, partials);
+        } else {
+            const size_t smem = ((size_t)2 * CN + tab) * sizeof(float);
+            launch(decode_kernel<NOBJ, true, false>, dim3(grid), dim3(kDecThreads), smem, st, d.H, consts, a, b, partials);
+        }
         int rc = check_launch("decode_bwd");
         if (rc) return rc;
         launch(decode_reduce_kernel, dim3(cdiv(CN, 256)), dim3(256), 0, st, (const float*)partials, grid, CN, d_consts,
@@ -298,7 +381,7 @@ static int run_decode(const Dims& d, const float* consts, const DecSeg& a, const
         return check_launch("decode_reduce");
     }
     const size_t smem = ((size_t)CN + tab) * sizeof(float);
-    launch(decode_kernel<NOBJ, false>, dim3(grid), dim3(kDecThreads), smem, st, d.H, consts, a, b, (float*)nullptr);
+    launch(decode_kernel<NOBJ, false, false>, dim3(grid), dim3(kDecThreads), smem, st, d.H, consts, a, b, (float*)nullptr);
     return check_launch("decode_fwd");
 }
 

@@ -224,7 +224,6 @@ def test_staged_host_input_step_equals_device_step():
                                               losses_host.data_ptr(), ws.data_ptr(), main.cuda_stream))
         main.synchronize()
         assert torch.equal(losses_host, want[slot][0])
-        # gradients agree to rounding: the decoder accumulates template gradients with shared-memory float atomics, whose
-        # order (not value) varies from launch to launch
-        got, ref = net.flat_gradients().detach().cpu()[:-4], want[slot][1][:-4]
-        assert (got - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+        # bit-identical: every reduction of the step runs in a fixed order (the decoder gathers template gradients
+        # instead of scattering them with float atomics)
+        assert torch.equal(net.flat_gradients().detach().cpu()[:-4], want[slot][1][:-4])
