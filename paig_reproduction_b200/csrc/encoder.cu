@@ -655,6 +655,221 @@ __global__ void __launch_bounds__(256) vel_scatter_kernel(const float* __restric
     }
 }
 
+// ---- fused VelocityEncoder MLP (blocks.py:43-48: Linear(2 in,100) tanh Linear(100,100) tanh Linear(100,2)) -------------
+// The problem is tiny (n B rows x 11 k MACs) and was 5 + 14 launch-latency-bound GEMM / gather / scatter launches; two
+// kernels do it: forward (8 rows per CTA, weights transposed into shared memory so unit j of a layer is lane j) also
+// gathers the inputs and writes the rollout's initial state; backward is ONE CTA that walks the rows in chunks of 8 and
+// keeps every weight-gradient entry in a register of its owning thread (fixed order => deterministic), then scatters the
+// input gradient into d enc_pos.
+constexpr int kVelRows = 8;
+constexpr int kVelMaxIn = 16;             // 2 * input_steps
+
+__global__ void __launch_bounds__(128) vel_mlp_fwd_kernel(const float* __restrict__ enc_pos, int B, int n, int e, int in,
+                                                          int steps, const float* __restrict__ W1, const float* __restrict__ b1,
+                                                          const float* __restrict__ W2, const float* __restrict__ b2,
+                                                          const float* __restrict__ W3, const float* __restrict__ b3,
+                                                          float* __restrict__ vin, float* __restrict__ v1, float* __restrict__ v2,
+                                                          float* __restrict__ vout, float* __restrict__ seq) {
+    constexpr int HID = kVelHidden;
+    PAIG_DYN_SMEM(float, smem);
+    float* sW2t = smem;                               // [k][j]
+    float* sW1t = sW2t + HID * HID;                   // [k][j]
+    float (*sIn)[kVelMaxIn] = reinterpret_cast<float (*)[kVelMaxIn]>(sW1t + kVelMaxIn * HID);
+    float (*sH1)[HID] = reinterpret_cast<float (*)[HID]>(&sIn[kVelRows][0]);
+    float (*sH2)[HID] = reinterpret_cast<float (*)[HID]>(&sH1[kVelRows][0]);
+    const int tid = threadIdx.x, cols = 2 * in, M = n * B;
+    const int r0 = blockIdx.x * kVelRows;
+    for (int i = tid; i < HID * HID; i += 128) sW2t[(i % HID) * HID + i / HID] = W2[i];
+    for (int i = tid; i < HID * cols; i += 128) sW1t[(i % cols) * HID + i / cols] = W1[i];
+    for (int i = tid; i < kVelRows * cols; i += 128) {
+        const int r = i / cols, col = i % cols, row = r0 + r;
+        float v = 0.f;
+        if (row < M) {
+            const int o = row / B, b = row % B, tau = col >> 1, c = col & 1;
+            v = enc_pos[((long)b * e + tau) * 2 * n + 2 * o + c];
+            vin[(long)row * cols + col] = v;
+        }
+        sIn[r][col] = v;
+    }
+    __syncthreads();
+    if (tid < HID) {
+        float acc[kVelRows];
+#pragma unroll
+        for (int r = 0; r < kVelRows; ++r) acc[r] = 0.f;
+        for (int k = 0; k < cols; ++k) {
+            const float w = sW1t[k * HID + tid];
+#pragma unroll
+            for (int r = 0; r < kVelRows; ++r) acc[r] += sIn[r][k] * w;
+        }
+        const float bb = b1[tid];
+#pragma unroll
+        for (int r = 0; r < kVelRows; ++r) {
+            const float h = tanhf(acc[r] + bb);
+            sH1[r][tid] = h;
+            if (r0 + r < M) v1[(long)(r0 + r) * HID + tid] = h;
+        }
+    }
+    __syncthreads();
+    if (tid < HID) {
+        float acc[kVelRows];
+#pragma unroll
+        for (int r = 0; r < kVelRows; ++r) acc[r] = 0.f;
+        for (int k = 0; k < HID; ++k) {
+            const float w = sW2t[k * HID + tid];
+#pragma unroll
+            for (int r = 0; r < kVelRows; ++r) acc[r] += sH1[r][k] * w;
+        }
+        const float bb = b2[tid];
+#pragma unroll
+        for (int r = 0; r < kVelRows; ++r) {
+            const float h = tanhf(acc[r] + bb);
+            sH2[r][tid] = h;
+            if (r0 + r < M) v2[(long)(r0 + r) * HID + tid] = h;
+        }
+    }
+    __syncthreads();
+    if (tid < kVelRows * 2) {
+        const int r = tid >> 1, c = tid & 1, row = r0 + r;
+        if (row < M) {
+            float s = 0.f;
+            for (int k = 0; k < HID; ++k) s += sH2[r][k] * W3[c * HID + k];
+            s += b3[c];
+            vout[(long)row * 2 + c] = s;
+            const int o = row / B, b = row % B;
+            float* sq = seq + (long)b * (steps + 1) * 4 * n;           // physics_models.py:225-228: [pos(in-1) | vel]
+            sq[2 * o + c] = enc_pos[((long)b * e + (in - 1)) * 2 * n + 2 * o + c];
+            sq[2 * n + 2 * o + c] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(512) vel_mlp_bwd_kernel(const float* __restrict__ d_state0, int B, int n, int e, int in,
+                                                          const float* __restrict__ W1, const float* __restrict__ W2,
+                                                          const float* __restrict__ W3, const float* __restrict__ vin,
+                                                          const float* __restrict__ v1, const float* __restrict__ v2,
+                                                          float* __restrict__ partials, int stride,
+                                                          float* __restrict__ d_enc_pos) {
+    constexpr int HID = kVelHidden, NT = 512, R = kVelRows;
+    constexpr int W2_PER = (HID * HID + NT - 1) / NT;                  // 20 entries of dW2 per thread
+    PAIG_DYN_SMEM(float, smem);
+    float* sW2 = smem;                                                 // [j][k]
+    float* sW1 = sW2 + HID * HID;
+    float* sW3 = sW1 + HID * kVelMaxIn;
+    float (*sH1)[HID] = reinterpret_cast<float (*)[HID]>(sW3 + 2 * HID);
+    float (*sH2)[HID] = reinterpret_cast<float (*)[HID]>(&sH1[R][0]);
+    float (*sDz2)[HID] = reinterpret_cast<float (*)[HID]>(&sH2[R][0]);
+    float (*sDz1)[HID] = reinterpret_cast<float (*)[HID]>(&sDz2[R][0]);
+    float (*sIn)[kVelMaxIn] = reinterpret_cast<float (*)[kVelMaxIn]>(&sDz1[R][0]);
+    float (*sDz3)[2] = reinterpret_cast<float (*)[2]>(&sIn[R][0]);
+    const int tid = threadIdx.x, cols = 2 * in, M = n * B;
+    for (int i = tid; i < HID * HID; i += NT) sW2[i] = W2[i];
+    for (int i = tid; i < HID * cols; i += NT) sW1[i] = W1[i];
+    for (int i = tid; i < 2 * HID; i += NT) sW3[i] = W3[i];
+    float aW2[W2_PER], aW1[4], aW3 = 0.f, ab = 0.f;                    // gradients owned by this thread
+#pragma unroll
+    for (int i = 0; i < W2_PER; ++i) aW2[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) aW1[i] = 0.f;
+    __syncthreads();
+    {
+        const int r0 = blockIdx.x * R;                                 // one chunk of rows per CTA
+        const int nr = min(R, M - r0);
+        for (int i = tid; i < R * HID; i += NT) {
+            const int r = i / HID, k = i % HID;
+            sH1[r][k] = r < nr ? v1[(long)(r0 + r) * HID + k] : 0.f;
+            sH2[r][k] = r < nr ? v2[(long)(r0 + r) * HID + k] : 0.f;
+        }
+        for (int i = tid; i < R * cols; i += NT) sIn[i / cols][i % cols] = i / cols < nr ? vin[(long)(r0 + i / cols) * cols + i % cols] : 0.f;
+        if (tid < R * 2) {
+            const int r = tid >> 1, c = tid & 1, row = r0 + r;
+            float v = 0.f;
+            if (r < nr) { const int o = row / B, b = row % B; v = d_state0[(long)b * 4 * n + 2 * n + 2 * o + c]; }
+            sDz3[r][c] = v;
+        }
+        __syncthreads();
+        // layer 3: dW3[c][k] (thread c*100+k), db3[c] (threads 200, 201); dz2 = (W3^T dz3) (1 - h2^2)
+        if (tid < 2 * HID) {
+            const int c = tid / HID, k = tid % HID;
+#pragma unroll
+            for (int r = 0; r < R; ++r) aW3 += sDz3[r][c] * sH2[r][k];
+        } else if (tid < 2 * HID + 2) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) ab += sDz3[r][tid - 2 * HID];
+        }
+        for (int i = tid; i < R * HID; i += NT) {
+            const int r = i / HID, k = i % HID;
+            const float h = sH2[r][k];
+            sDz2[r][k] = (sW3[k] * sDz3[r][0] + sW3[HID + k] * sDz3[r][1]) * (1.f - h * h);
+        }
+        __syncthreads();
+        // layer 2: dW2 entries e = tid + 512 i -> (j, k); db2[j] (threads 256..355); dz1 = (W2^T dz2) (1 - h1^2)
+#pragma unroll
+        for (int i = 0; i < W2_PER; ++i) {
+            const int en = tid + NT * i;
+            if (en < HID * HID) {
+                const int j = en / HID, k = en % HID;
+                float s = aW2[i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) s += sDz2[r][j] * sH1[r][k];
+                aW2[i] = s;
+            }
+        }
+        if (tid >= 256 && tid < 256 + HID) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) ab += sDz2[r][tid - 256];
+        }
+        for (int i = tid; i < R * HID; i += NT) {
+            const int r = i / HID, k = i % HID;
+            float s = 0.f;
+            for (int j = 0; j < HID; ++j) s += sW2[j * HID + k] * sDz2[r][j];
+            const float h = sH1[r][k];
+            sDz1[r][k] = s * (1.f - h * h);
+        }
+        __syncthreads();
+        // layer 1: dW1 entries e = tid + 512 i < 100 cols; db1[j] (threads 384..483); d vin scattered into d enc_pos
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int en = tid + NT * i;
+            if (en < HID * cols) {
+                const int j = en / cols, k = en % cols;
+                float s = aW1[i];
+#pragma unroll
+                for (int r = 0; r < R; ++r) s += sDz1[r][j] * sIn[r][k];
+                aW1[i] = s;
+            }
+        }
+        if (tid >= 384 && tid < 384 + HID) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) ab += sDz1[r][tid - 384];
+        }
+        if (tid < R * cols) {
+            const int r = tid / cols, col = tid % cols, row = r0 + r;
+            if (r < nr) {
+                float s = 0.f;
+                for (int j = 0; j < HID; ++j) s += sW1[j * cols + col] * sDz1[r][j];
+                const int o = row / B, b = row % B, tau = col >> 1, c = col & 1;
+                // the position half of d state0 goes to d enc_pos[b, in-1, :] (physics_models.py:225): same owner
+                if (tau == in - 1) s += d_state0[(long)b * 4 * n + 2 * o + c];
+                d_enc_pos[((long)b * e + tau) * 2 * n + 2 * o + c] += s;     // each (b, tau, o, c) has one owner
+            }
+        }
+        __syncthreads();
+    }
+    // this CTA's partial sums: [dW2 | dW1 | dW3 | db1 | db2 | db3], folded in fixed order by reduce_partials_batch
+    float* out = partials + (size_t)blockIdx.x * stride;
+    float* oW1 = out + HID * HID, *oW3 = oW1 + HID * cols, *ob1 = oW3 + 2 * HID, *ob2 = ob1 + HID, *ob3 = ob2 + HID;
+    if (tid < 2 * HID) oW3[tid] = aW3;
+    else if (tid < 2 * HID + 2) ob3[tid - 2 * HID] = ab;
+    if (tid >= 256 && tid < 256 + HID) ob2[tid - 256] = ab;
+    if (tid >= 384 && tid < 384 + HID) ob1[tid - 384] = ab;
+#pragma unroll
+    for (int i = 0; i < W2_PER; ++i)
+        if (tid + NT * i < HID * HID) out[tid + NT * i] = aW2[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (tid + NT * i < HID * cols) oW1[tid + NT * i] = aW1[i];
+}
+
 int velocity_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* enc_pos, float* ws,
                      cudaStream_t st) {
     const Dims& d = L.d;
@@ -663,6 +878,16 @@ int velocity_forward(const paig_task* t, const paig_params* p, const Layout& L, 
     const float* vout = nullptr;
     if (d.in > 1) {                                                   // physics_models.py:220-223
         const int M = d.n * L.B, cols = t->alt_vel ? 2 * (d.in - 1) : 2 * d.in;
+        static const bool vel_gemm = getenv("PAIG_VEL_GEMM") != nullptr;
+        if (!t->alt_vel && !vel_gemm && cols <= kVelMaxIn) {            // one fused launch (gather + MLP + initial state)
+            const size_t smem = ((size_t)kVelHidden * kVelHidden + (size_t)kVelMaxIn * kVelHidden +
+                                 (size_t)kVelRows * (kVelMaxIn + 2 * kVelHidden)) * sizeof(float);
+            launch(vel_mlp_fwd_kernel, dim3(cdiv(M, kVelRows)), dim3(128), smem, st, enc_pos, L.B, d.n, d.e, d.in, d.steps,
+                   (const float*)p->vel[0].w, (const float*)p->vel[0].b, (const float*)p->vel[1].w, (const float*)p->vel[1].b,
+                   (const float*)p->vel[2].w, (const float*)p->vel[2].b, ws + L.vin, ws + L.v1, ws + L.v2, ws + L.vout,
+                   ws + L.seq);
+            return check_launch("vel_mlp_fwd");
+        }
         launch(vel_gather_kernel, dim3(cdiv(M * cols, 256)), dim3(256), 0, st, enc_pos, L.B, d.n, d.e, d.in,
                (int)t->alt_vel, ws + L.vin);
         if ((rc = check_launch("vel_gather"))) return rc;
@@ -688,6 +913,31 @@ int velocity_backward(const paig_task* t, const paig_params* p, const paig_param
     if (L.B <= 0) return 0;
     int rc;
     const bool has_vel = d.in > 1;
+    {
+        static const bool vel_gemm = getenv("PAIG_VEL_GEMM") != nullptr;
+        const int M = d.n * L.B, cols = 2 * d.in;
+        const int HID = kVelHidden;
+        const int stride = HID * HID + HID * cols + 2 * HID + 2 * HID + 2 + 2;          // floats per CTA partial (padded)
+        const int ctas = cdiv(M, kVelRows);
+        if (has_vel && !t->alt_vel && !vel_gemm && cols <= kVelMaxIn && (size_t)ctas * stride <= L.partials_floats) {
+            const size_t smem = ((size_t)HID * HID + (size_t)HID * kVelMaxIn + 2 * HID +
+                                 (size_t)kVelRows * (4 * HID + kVelMaxIn + 2)) * sizeof(float);
+            float* part = ws + L.partials;
+            launch(vel_mlp_bwd_kernel, dim3(ctas), dim3(512), smem, st, d_state0, L.B, d.n, d.e, d.in, (const float*)p->vel[0].w,
+                   (const float*)p->vel[1].w, (const float*)p->vel[2].w, (const float*)(ws + L.vin), (const float*)(ws + L.v1),
+                   (const float*)(ws + L.v2), part, stride, d_enc_pos);
+            if ((rc = check_launch("vel_mlp_bwd"))) return rc;
+            ReduceBatch folds;                                        // (NULL destinations: that gradient is not wanted)
+            const float* pW1 = part + HID * HID, *pW3 = pW1 + HID * cols, *pb1 = pW3 + 2 * HID, *pb2 = pb1 + HID, *pb3 = pb2 + HID;
+            if (g->vel[1].w) folds.add(part, ctas, stride, HID * HID, g->vel[1].w, 0, nullptr);
+            if (g->vel[0].w) folds.add(pW1, ctas, stride, HID * cols, g->vel[0].w, 0, nullptr);
+            if (g->vel[2].w) folds.add(pW3, ctas, stride, 2 * HID, g->vel[2].w, 0, nullptr);
+            if (g->vel[0].b) folds.add(pb1, ctas, stride, HID, g->vel[0].b, 0, nullptr);
+            if (g->vel[1].b) folds.add(pb2, ctas, stride, HID, g->vel[1].b, 0, nullptr);
+            if (g->vel[2].b) folds.add(pb3, ctas, stride, 2, g->vel[2].b, 0, nullptr);
+            return reduce_partials_batch(folds, st);
+        }
+    }
     launch(state0_bwd_kernel, dim3(cdiv(L.B * 4 * d.n, 256)), dim3(256), 0, st, d_state0, L.B, d.n, d.e, d.in, d_enc_pos,
            has_vel ? ws + L.dvout : (float*)nullptr);
     if ((rc = check_launch("state0_bwd"))) return rc;
