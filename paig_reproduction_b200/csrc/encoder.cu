@@ -471,6 +471,141 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(const float4* __rest
     out[idx] = x[(f / fps) * seq_stride4 + (f % fps) * chw4 + r];
 }
 
+// ---- fused tail of the localisation MLP: relu(l2) -> l3 -> tanh * H/2 + H/2  (blocks.py:99-102) ----------------------
+// After the big l1 product the rest of the MLP is small (M x 200 x 200 and M x 200 x 2) and was three launches forward
+// and nine backward.  Forward: 16 rows per CTA, W2 transposed into shared memory (lane j = unit j).  Backward: 16 rows per
+// CTA write their share of dW2 / dW3 / db2 / db3 to a partial block (folded in fixed order by reduce_partials_batch)
+// and dH1 (gated by l1's ReLU) for the l1 backward GEMMs.
+constexpr int kTailRows = 16;
+
+__global__ void __launch_bounds__(256) enc_tail_fwd_kernel(const float* __restrict__ H1, int M, int N, int n, float half,
+                                                           const float* __restrict__ W2, const float* __restrict__ b2,
+                                                           const float* __restrict__ W3, const float* __restrict__ b3,
+                                                           float* __restrict__ H2, float* __restrict__ O3,
+                                                           float* __restrict__ enc_pos, float* __restrict__ enc_pos2) {
+    constexpr int HID = kHidden, R = kTailRows;
+    PAIG_DYN_SMEM(float, smem);
+    float* sW2t = smem;                                   // [k][j]
+    float (*sH1)[HID] = reinterpret_cast<float (*)[HID]>(sW2t + HID * HID);
+    float (*sH2)[HID] = reinterpret_cast<float (*)[HID]>(&sH1[R][0]);
+    const int tid = threadIdx.x, r0 = blockIdx.x * R;
+    for (int i = tid; i < HID * HID; i += 256) sW2t[(i % HID) * HID + i / HID] = W2[i];
+    for (int i = tid; i < R * HID; i += 256) sH1[i / HID][i % HID] = r0 + i / HID < M ? H1[(long)(r0 + i / HID) * HID + i % HID] : 0.f;
+    __syncthreads();
+    if (tid < HID) {
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        for (int k = 0; k < HID; ++k) {
+            const float w = sW2t[k * HID + tid];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] += sH1[r][k] * w;
+        }
+        const float bb = b2[tid];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const float h = fmaxf(acc[r] + bb, 0.f);
+            sH2[r][tid] = h;
+            if (r0 + r < M) H2[(long)(r0 + r) * HID + tid] = h;
+        }
+    }
+    __syncthreads();
+    if (tid < R * 2) {
+        const int r = tid >> 1, c = tid & 1, row = r0 + r;
+        if (row < M) {
+            float s = 0.f;
+            for (int k = 0; k < HID; ++k) s += sH2[r][k] * W3[c * HID + k];
+            s += b3[c];
+            O3[(long)row * 2 + c] = s;
+            const int o = row / N, f = row % N;                       // rows are object-major (blocks.py:88-93)
+            const float v = tanhf(s) * half + half;
+            enc_pos[(long)f * 2 * n + 2 * o + c] = v;
+            if (enc_pos2) enc_pos2[(long)f * 2 * n + 2 * o + c] = v;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) enc_tail_bwd_kernel(const float* __restrict__ d_enc_pos, int M, int N, int n, float half,
+                                                           const float* __restrict__ W2, const float* __restrict__ W3,
+                                                           const float* __restrict__ H1, const float* __restrict__ H2,
+                                                           const float* __restrict__ O3, float* __restrict__ dH1,
+                                                           float* __restrict__ partials, int stride) {
+    constexpr int HID = kHidden, R = kTailRows;
+    PAIG_DYN_SMEM(float, smem);
+    float* sW2 = smem;                                    // [j][k]
+    float (*sH1)[HID] = reinterpret_cast<float (*)[HID]>(sW2 + HID * HID);
+    float (*sH2)[HID] = reinterpret_cast<float (*)[HID]>(&sH1[R][0]);
+    float (*sDz2)[HID] = reinterpret_cast<float (*)[HID]>(&sH2[R][0]);
+    float (*sDo3)[2] = reinterpret_cast<float (*)[2]>(&sDz2[R][0]);
+    const int tid = threadIdx.x, r0 = blockIdx.x * R;
+    for (int i = tid; i < HID * HID; i += 256) sW2[i] = W2[i];
+    for (int i = tid; i < R * HID; i += 256) {
+        const int r = i / HID, k = i % HID;
+        const bool ok = r0 + r < M;
+        sH1[r][k] = ok ? H1[(long)(r0 + r) * HID + k] : 0.f;
+        sH2[r][k] = ok ? H2[(long)(r0 + r) * HID + k] : 0.f;
+    }
+    if (tid < R * 2) {
+        const int r = tid >> 1, c = tid & 1, row = r0 + r;
+        float v = 0.f;
+        if (row < M) {
+            const int o = row / N, f = row % N;
+            const float th = tanhf(O3[(long)row * 2 + c]);
+            v = d_enc_pos[(long)f * 2 * n + 2 * o + c] * half * (1.f - th * th);
+        }
+        sDo3[r][c] = v;
+    }
+    __syncthreads();
+    float* out = partials + (size_t)blockIdx.x * stride;          // [dW2 | dW3 | db2 | db3]
+    float* oW3 = out + HID * HID, *ob2 = oW3 + 2 * HID, *ob3 = ob2 + HID;
+    // dZ2 = (W3^T dO3) gated by l2's ReLU
+    for (int i = tid; i < R * HID; i += 256) {
+        const int r = i / HID, k = i % HID;
+        const float d = W3[k] * sDo3[r][0] + W3[HID + k] * sDo3[r][1];
+        sDz2[r][k] = sH2[r][k] > 0.f ? d : 0.f;
+    }
+    for (int i = tid; i < 2 * HID; i += 256) {
+        const int c = i / HID, k = i % HID;
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s += sDo3[r][c] * sH2[r][k];
+        oW3[i] = s;
+    }
+    if (tid < 2) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s += sDo3[r][tid];
+        ob3[tid] = s;
+    }
+    __syncthreads();
+    for (int i = tid; i < HID * HID; i += 256) {                  // this chunk's share of dW2[j][k]
+        const int j = i / HID, k = i % HID;
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s += sDz2[r][j] * sH1[r][k];
+        out[i] = s;
+    }
+    if (tid < HID) {
+        float s = 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) s += sDz2[r][tid];
+        ob2[tid] = s;
+    }
+    // dH1 = (dZ2 W2) gated by l1's ReLU
+    for (int i = tid; i < R * HID; i += 256) {
+        const int r = i / HID, k = i % HID;
+        if (r0 + r >= M) continue;
+        float s = 0.f;
+        for (int j = 0; j < HID; ++j) s += sW2[j * HID + k] * sDz2[r][j];
+        dH1[(long)(r0 + r) * HID + k] = sH1[r][k] > 0.f ? s : 0.f;
+    }
+}
+
+static size_t enc_tail_smem(bool bwd) {
+    return ((size_t)kHidden * kHidden + (size_t)kTailRows * kHidden * (bwd ? 3 : 2) + (bwd ? kTailRows * 2 : 0)) * sizeof(float);
+}
+constexpr int kTailStride = kHidden * kHidden + 2 * kHidden + kHidden + 4;      // floats per CTA partial
+
 int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride,
                     int fps, float* enc_pos_out, float* enc_masks_out, float* masked_out, float* ws, cudaStream_t st) {
     const Dims& d = L.d;
@@ -522,6 +657,13 @@ int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, c
                                         ws + L.partials, L.partials_floats, "sgemm_l1_fwd")))
             return rc;
     }
+    static const bool tail_gemm = getenv("PAIG_TAIL_GEMM") != nullptr;
+    if (!tail_gemm) {                                  // l2 + l3 + position head in one launch
+        launch(enc_tail_fwd_kernel, dim3(cdiv(M, kTailRows)), dim3(256), enc_tail_smem(false), st, (const float*)(ws + L.H1), M,
+               L.N, d.n, (float)d.H * 0.5f, (const float*)p->enc_l2.w, (const float*)p->enc_l2.b, (const float*)p->enc_l3.w,
+               (const float*)p->enc_l3.b, ws + L.H2, ws + L.O3, ws + L.enc_pos, enc_pos_out);
+        return check_launch("enc_tail_fwd");
+    }
     if ((rc = linear_forward(ws + L.H1, p->enc_l2.w, p->enc_l2.b, ws + L.H2, M, kHidden, kHidden, EPI_RELU, st)))
         return rc;
     if ((rc = linear_forward(ws + L.H2, p->enc_l3.w, p->enc_l3.b, ws + L.O3, M, kHidden, 2, EPI_NONE, st))) return rc;
@@ -537,6 +679,23 @@ int encoder_backward(const paig_task* t, const paig_params* p, const paig_params
     if (L.N <= 0) return 0;
     int rc;
     const int M = d.n * L.N;
+    static const bool tail_gemm = getenv("PAIG_TAIL_GEMM") != nullptr;
+    const int tail_ctas = cdiv(M, kTailRows);
+    if (!tail_gemm && (size_t)tail_ctas * kTailStride <= L.partials_floats) {
+        // position head + l3 + l2 backward in one launch; per-CTA partials folded in fixed order
+        float* part = ws + L.partials;
+        launch(enc_tail_bwd_kernel, dim3(tail_ctas), dim3(256), enc_tail_smem(true), st, d_enc_pos, M, L.N, d.n,
+               (float)d.H * 0.5f, (const float*)p->enc_l2.w, (const float*)p->enc_l3.w, (const float*)(ws + L.H1),
+               (const float*)(ws + L.H2), (const float*)(ws + L.O3), ws + L.dH1, part, kTailStride);
+        if ((rc = check_launch("enc_tail_bwd"))) return rc;
+        ReduceBatch folds;
+        const float* pW3 = part + kHidden * kHidden, *pb2 = pW3 + 2 * kHidden, *pb3 = pb2 + kHidden;
+        if (g->enc_l2.w) folds.add(part, tail_ctas, kTailStride, kHidden * kHidden, g->enc_l2.w, 0, nullptr);
+        if (g->enc_l3.w) folds.add(pW3, tail_ctas, kTailStride, 2 * kHidden, g->enc_l3.w, 0, nullptr);
+        if (g->enc_l2.b) folds.add(pb2, tail_ctas, kTailStride, kHidden, g->enc_l2.b, 0, nullptr);
+        if (g->enc_l3.b) folds.add(pb3, tail_ctas, kTailStride, 2, g->enc_l3.b, 0, nullptr);
+        if ((rc = reduce_partials_batch(folds, st))) return rc;
+    } else {
     launch(pos_head_bwd_kernel, dim3(cdiv(L.N * 2 * d.n, 256)), dim3(256), 0, st, (const float*)(ws + L.O3), L.N, d.n,
            (float)d.H * 0.5f, d_enc_pos, ws + L.dO3);
     if ((rc = check_launch("pos_head_bwd"))) return rc;
@@ -551,6 +710,7 @@ int encoder_backward(const paig_task* t, const paig_params* p, const paig_params
         return rc;
     if ((rc = linear_dgrad(ws + L.dH2, p->enc_l2.w, ws + L.dH1, M, kHidden, kHidden, EPI_MASK_RELU, ws + L.H1, st)))
         return rc;
+    }
     // l1
     {
         float* Wt = ws + L.tc_scratch;                       // [K][200]
