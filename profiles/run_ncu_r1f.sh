@@ -1,6 +1,7 @@
 #!/bin/bash
-# Round-1 final captures: launch list of one step, then full captures of the three dominant kernels and of the
-# decoder / rollout kernels the north star names.  Run under gpurun from the repo root.
+# Round-1 final captures: launch list of one step, then full captures of the three dominant kernels, of the
+# decoder / rollout kernels the north star names, and of the GEMM / MLP kernels (fp32 l1 forward, tcgen05 l1 backward,
+# fused MLP tails).  Run under gpurun from the repo root.
 set -e
 TAG=r1f
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
@@ -17,5 +18,7 @@ cap fused_bwd unet_fused_bwd 3 1
 cap wgrad wgrad_tma 36 12
 cap decode "decode_" 6 2
 cap rollout "rollout_" 6 2
-cap sgemm sgemm_kernel 54 18
+cap sgemm sgemm_kernel 3 1
+cap tc gemm_tf32x3 6 2
+cap tail "enc_tail|vel_mlp" 12 4
 du -sh gpurun_out
