@@ -583,6 +583,73 @@ __global__ void __launch_bounds__(256) conv1x1_bwd_kernel(const float* __restric
     }
 }
 
+// Weight / bias gradient only (the fused backward-data kernel owns d in): a CTA walks whole frames, a thread owns four
+// consecutive pixels (16-byte loads, 32-bit indexing), per-CTA partial at the end as in conv1x1_bwd_kernel.
+template <int CIN>
+__global__ void __launch_bounds__(256) conv1x1_wgrad_kernel(const float* __restrict__ in, long in_bs,
+                                                            const float* __restrict__ dout, long dout_bs,
+                                                            const float* __restrict__ act, long act_bs, int Cout, int HW,
+                                                            int N, float* __restrict__ partials) {
+    __shared__ float red[8][kMaxObjs * (kMaxHeadIn + 1)];
+    float aw[kMaxObjs][CIN], ab[kMaxObjs];
+#pragma unroll
+    for (int o = 0; o < kMaxObjs; ++o) {
+        ab[o] = 0.f;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) aw[o][c] = 0.f;
+    }
+    const int q4 = HW / 4;
+    for (int f = blockIdx.x; f < N; f += gridDim.x) {
+        const float* inf = in + (long)f * in_bs;
+        const float* gf = dout + (long)f * dout_bs;
+        const float* af = act ? act + (long)f * act_bs : nullptr;
+        for (int q = threadIdx.x; q < q4; q += 256) {
+            float4 g[kMaxObjs];
+#pragma unroll
+            for (int o = 0; o < kMaxObjs; ++o) {
+                g[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (o < Cout) {
+                    g[o] = *reinterpret_cast<const float4*>(gf + o * HW + 4 * q);
+                    if (af) {
+                        const float4 a = *reinterpret_cast<const float4*>(af + o * HW + 4 * q);
+                        g[o].x = a.x > 0.f ? g[o].x : 0.f; g[o].y = a.y > 0.f ? g[o].y : 0.f;
+                        g[o].z = a.z > 0.f ? g[o].z : 0.f; g[o].w = a.w > 0.f ? g[o].w : 0.f;
+                    }
+                    ab[o] += (g[o].x + g[o].y) + (g[o].z + g[o].w);
+                }
+            }
+            float4 v[CIN];
+#pragma unroll
+            for (int c = 0; c < CIN; ++c) v[c] = *reinterpret_cast<const float4*>(inf + c * HW + 4 * q);
+#pragma unroll
+            for (int c = 0; c < CIN; ++c)
+#pragma unroll
+                for (int o = 0; o < kMaxObjs; ++o)
+                    if (o < Cout) aw[o][c] += (g[o].x * v[c].x + g[o].y * v[c].y) + (g[o].z * v[c].z + g[o].w * v[c].w);
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 0; o < kMaxObjs; ++o) {
+#pragma unroll
+        for (int c = 0; c < CIN; ++c) {
+            const float s = warp_sum(aw[o][c]);
+            if (lane == 0) red[wid][o * (kMaxHeadIn + 1) + c] = s;
+        }
+        const float sb = warp_sum(ab[o]);
+        if (lane == 0) red[wid][o * (kMaxHeadIn + 1) + kMaxHeadIn] = sb;
+    }
+    __syncthreads();
+    const int nW = Cout * CIN;
+    for (int e = threadIdx.x; e < nW + Cout; e += blockDim.x) {
+        const int o = e < nW ? e / CIN : e - nW, c = e < nW ? e % CIN : kMaxHeadIn;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += red[k][o * (kMaxHeadIn + 1) + c];
+        partials[(size_t)blockIdx.x * (nW + Cout) + e] = s;
+    }
+}
+
 int conv1x1_forward(const float* in, long in_bs, int Cin, const float* w, const float* b, float* out, long out_bs,
                     int Cout, int S, int N, int relu, cudaStream_t st) {
     if (Cin > kMaxHeadIn || Cout > kMaxObjs) {
@@ -603,6 +670,19 @@ int conv1x1_backward(const float* in, long in_bs, int Cin, const float* w, const
     }
     int blocks = cdiv((long)N * S * S, 256 * 4);
     if (blocks > 592) blocks = 592;
+    const bool vec = !din && (S * S) % 4 == 0 && (in_bs % 4) == 0 && (dout_bs % 4) == 0 && (!act || act_bs % 4 == 0) &&
+                     ((uintptr_t)in % 16) == 0 && ((uintptr_t)dout % 16) == 0 && (!act || (uintptr_t)act % 16 == 0);
+    if (vec && (Cin == 8 || Cin == 16)) {
+        blocks = N < 592 ? N : 592;
+        if (Cin == 8) launch(conv1x1_wgrad_kernel<8>, dim3(blocks), dim3(256), 0, st, in, in_bs, dout, dout_bs, act, act_bs, Cout,
+                             S * S, N, partials);
+        else launch(conv1x1_wgrad_kernel<16>, dim3(blocks), dim3(256), 0, st, in, in_bs, dout, dout_bs, act, act_bs, Cout,
+                    S * S, N, partials);
+        int rc = check_launch("conv1x1_bwd");
+        if (rc) return rc;
+        if (defer) return defer->add(partials, blocks, Cout * Cin + Cout, Cout * Cin, dW, Cout, db) ? 0 : 1;
+        return reduce_partials(partials, blocks, Cout * Cin + Cout, Cout * Cin, dW, Cout, db, st);
+    }
     launch(conv1x1_bwd_kernel, dim3(blocks), dim3(256), 0, st, in, in_bs, Cin, w, dout, dout_bs, act, act_bs, Cout,
            S * S, N, din, din_bs, partials);
     int rc = check_launch("conv1x1_bwd");
