@@ -368,8 +368,17 @@ static int run_decode(const Dims& d, const float* consts, const DecSeg& a, const
         const size_t gather_fl = (size_t)NOBJ * 4 * (d.HW + d.H * d.t) + (size_t)2 * NOBJ * d.t * 8;
         const size_t smem_g = ((size_t)2 * CN + tab + gather_fl) * sizeof(float);
         static const bool atomics = getenv("PAIG_DECODE_ATOMICS") != nullptr;
-        if (!atomics && smem_g <= 110 * 1024) {             // two CTAs per SM
-            launch(decode_kernel<NOBJ, true, true>, dim3(grid), dim3(kDecThreads), smem_g, st, d.H, consts, a, b, partials);
+        // Three objects need > 200 registers per thread: one CTA per SM whatever the shared-memory footprint, so the
+        // gather tables may take the whole SM (3bp, 36 px: 162 KB) and the grid is one CTA per SM.
+        const bool one_cta = NOBJ >= 3;
+        if (!atomics && smem_g <= (size_t)(one_cta ? 220 : 110) * 1024) {
+            const int g1 = one_cta && grid > 148 ? 148 : grid;
+            launch(decode_kernel<NOBJ, true, true>, dim3(g1), dim3(kDecThreads), smem_g, st, d.H, consts, a, b, partials);
+            int rc = check_launch("decode_bwd");
+            if (rc) return rc;
+            launch(decode_reduce_kernel, dim3(cdiv(CN, 256)), dim3(256), 0, st, (const float*)partials, g1, CN, d_consts,
+                   accumulate);
+            return check_launch("decode_reduce");
         } else {
             const size_t smem = ((size_t)2 * CN + tab) * sizeof(float);
             launch(decode_kernel<NOBJ, true, false>, dim3(grid), dim3(kDecThreads), smem, st, d.H, consts, a, b, partials);

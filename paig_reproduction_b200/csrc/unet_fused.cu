@@ -49,6 +49,7 @@ struct FusedOp {
     const float* gmask; long gmask_bs;    // activation whose sign gates the result (ReLU adjoint); F_POOLT: the pooled tensor's source
     const float* gsrc; long gsrc_bs;      // F_HEADT: upstream gradient of the logits
     const float* gmask2; long gmask2_bs;  // F_HEADT: the logits (head ReLU), nullable
+    int acc_gout;                         // F_POOLT: the other reader's share was parked in gout (global), not in1
 };
 struct FusedPlan {
     int nops, N, fps, H, first_w;
@@ -542,14 +543,20 @@ __device__ __forceinline__ void run_poolT(const FusedOp& op, float* sm, int f, i
         const int e = wk % per, sub = wk / per;
         const int y = e / So, x = e % So;
         for (int cb = sub; cb < C; cb += 4 * nsub) {                  // 4 channels per trip: their source loads overlap
-            float2 xa[4], xb[4];
+            float2 xa[4], xb[4], pa[4], pb[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int c = cb + u * nsub;
+                pa[u] = pb[u] = make_float2(0.f, 0.f);
                 if (c < C) {
                     const float* xs = op.gmask + (long)f * op.gmask_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
                     xa[u] = *reinterpret_cast<const float2*>(xs);
                     xb[u] = *reinterpret_cast<const float2*>(xs + Si);
+                    if (op.acc_gout) {                                 // share of the other reader, parked in HBM/L2
+                        const float* ps = op.gout + (long)f * op.gout_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
+                        pa[u] = *reinterpret_cast<const float2*>(ps);
+                        pb[u] = *reinterpret_cast<const float2*>(ps + Si);
+                    }
                 } else {
                     xa[u] = xb[u] = make_float2(0.f, 0.f);
                 }
@@ -570,8 +577,10 @@ __device__ __forceinline__ void run_poolT(const FusedOp& op, float* sm, int f, i
                 const long g00 = (long)f * op.gout_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
                 const long goff[4] = {g00, g00 + 1, g00 + Si, g00 + Si + 1};
 #pragma unroll
+                const float parked[4] = {pa[u].x, pa[u].y, pb[u].x, pb[u].y};
+#pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    float r = op.in1 >= 0 ? sm[op.in1 + toff[k]] : 0.f;
+                    float r = op.in1 >= 0 ? sm[op.in1 + toff[k]] : parked[k];
                     if (k == best) r += g;
                     if (op.relu && !(v[k] > 0.f)) r = 0.f;
                     if (op.out >= 0) sm[op.out + toff[k]] = r;
@@ -1066,7 +1075,11 @@ static long wpack_bwd_base(const UNetDesc& u) { return (long)(unet_wpack_floats(
 // Backward-data pass of the UNet in one persistent kernel.  Expects d_logits in the workspace; writes the ReLU-gated
 // gradient of every conv output into the workspace gradient buffers (what conv3x3_wgrad reads).  Returns -1 when
 // the network or its pattern of skip connections is not supported (caller runs the per-layer kernels).
-int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st) {
+// park_global: a skip connection's gradient waits for the max-pool adjoint in the workspace gradient buffer (L2)
+// instead of on chip -- 8-16 planes less shared memory, which is what lets the 36-px frames of 3bp fit.
+// Returns -2 when the plan needs more shared memory than an SM has.
+static int fused_backward_plan(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st,
+                               bool park_global) {
     const UNetDesc& u = L.unet;
     const Dims& d = L.d;
     FusedPlan P;
@@ -1120,9 +1133,9 @@ int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& 
     };
 
     // gradient slices on chip, one per producer slice
-    struct GS { int born, last, off, floats, parked; };
+    struct GS { int born, last, off, floats, parked, in_hbm; };
     GS gs[40];
-    for (int k = 0; k < npr; ++k) gs[k] = GS{-1, -1, -1, 0, 0};
+    for (int k = 0; k < npr; ++k) gs[k] = GS{-1, -1, -1, 0, 0, 0};
     int in0_of[kFusedMaxOps], in1_of[kFusedMaxOps], out_of[kFusedMaxOps];
     int nf = 0, nl = 0;
     long woff = wpack_bwd_base(u);
@@ -1177,7 +1190,8 @@ int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& 
             fo->gmask = act_ptr(pr[a], &fo->gmask_bs);           // source values: arg-max and ReLU gate
             if (pr[a].kind == OP_CONV) fo->gout = grad_ptr(pr[a], &fo->gout_bs);
             in0_of[nf] = kp; gs[kp].last = nf;
-            if (gs[a].born >= 0) { in1_of[nf] = a; gs[a].last = nf; }   // parked contribution of the other reader
+            if (gs[a].born >= 0 && gs[a].in_hbm) { fo->acc_gout = 1; gs[a].born = nf; gs[a].in_hbm = 0; }
+            else if (gs[a].born >= 0) { in1_of[nf] = a; gs[a].last = nf; }   // parked contribution of the other reader
             else gs[a].born = nf;
             out_of[nf] = a;
             gs[a].parked = 0;
@@ -1227,6 +1241,12 @@ int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& 
             } else if (pr[k].readers == 2 && gs[k].born < 0) {
                 finish(fo, k, false);                    // parked until the max-pool adjoint adds its share
                 gs[k].parked = 1;
+                if (park_global) {                       // ... in the gradient buffer the adjoint finalises in place
+                    if (pr[k].kind != OP_CONV) return -1;
+                    fo->gout = grad_ptr(pr[k], &fo->gout_bs);
+                    gs[k].in_hbm = 1;
+                    out_of[nf] = -1;
+                }
                 ++nf;
             } else {
                 return -1;
@@ -1282,7 +1302,7 @@ int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& 
                     fo.gout != nullptr, fo.wsm, fo.wfloats);
         }
     }
-    if ((size_t)peak * sizeof(float) > kFusedSmemLimit) return -1;
+    if ((size_t)peak * sizeof(float) > kFusedSmemLimit) return -2;
     P.N = L.N; P.fps = 1; P.H = d.H;
     float* wpack = ws + L.wpack;
     P.wpack = wpack;
@@ -1300,6 +1320,12 @@ int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& 
     if (debug && !rc) print_timing("fused UNet backward-data", P, grid, L.N, st);
 #endif
     return rc;
+}
+
+int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st) {
+    int rc = fused_backward_plan(t, p, L, ws, st, false);
+    if (rc == -2) rc = fused_backward_plan(t, p, L, ws, st, true);
+    return rc == -2 ? -1 : rc;
 }
 
 }  // namespace paig
