@@ -1,4 +1,6 @@
 // extern "C" surface of libpaig_b200.so (declared in include/paig_b200.h).
+#include <cstring>
+#include <cstdlib>
 #include "internal.h"
 
 #include <map>
@@ -50,6 +52,22 @@ void prof_before(cudaStream_t) {}
 void prof_after(cudaStream_t) {}
 static void prof_name(const char*) {}
 #endif
+
+// PAIG_PROFILE_LAYERS=1: per-layer names ("conv3x3_wgrad_tma 16->16@32") in the paig_profile_end report instead of
+// one line per kernel family.  Names are interned so the pointers stay valid for the profile records.
+const char* layer_name(const char* family, int Cin, int Cout, int S) {
+    static const bool on = getenv("PAIG_PROFILE_LAYERS") != nullptr;
+    if (!on) return family;
+    static char pool[256][48];
+    static int used = 0;
+    char tmp[48];
+    snprintf(tmp, sizeof(tmp), "%s_%d->%d@%d", family, Cin, Cout, S);
+    for (int i = 0; i < used; ++i)
+        if (!strcmp(pool[i], tmp)) return pool[i];
+    if (used == 256) return family;
+    strcpy(pool[used], tmp);
+    return pool[used++];
+}
 
 int check_launch(const char* what) {
     prof_name(what);

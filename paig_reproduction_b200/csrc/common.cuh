@@ -21,6 +21,7 @@ constexpr int kMaxObjs = 3;
 
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);
+const char* layer_name(const char* family, int Cin, int Cout, int S);   // per-layer profile names (PAIG_PROFILE_LAYERS)
 
 struct Dims {
     int n, H, t, e, in, pr, T, steps, HW, CHW;

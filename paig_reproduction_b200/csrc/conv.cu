@@ -229,7 +229,7 @@ int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
             else launch(conv3x3_kernel<8, -1>, grid, blk, smem, st, a);
     }
 #undef PAIG_CONV_CASE
-    return check_launch("conv3x3");
+    return check_launch(layer_name("conv3x3", a.Cin, a.Cout, a.S));
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -467,7 +467,7 @@ int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t s
         case 4: launch(conv3x3_wgrad_kernel<4>, wg_grid, wg_blk, smem, st, a); break;
         default: launch(conv3x3_wgrad_kernel<-1>, wg_grid, wg_blk, smem, st, a);
     }
-    int rc = check_launch("conv3x3_wgrad");
+    int rc = check_launch(layer_name("conv3x3_wgrad", a.Cin, a.Cout, a.S));
     if (rc) return rc;
     const int nW = a.Cout * a.Cin * 9;
     if (a.defer) return a.defer->add(a.partials, ctas, nW + a.Cout, nW, dW, a.Cout, db) ? 0 : 1;

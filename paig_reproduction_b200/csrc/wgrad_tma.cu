@@ -38,35 +38,35 @@ struct TmaView {                 // what the tensor map describes (also drives t
     const float* base;           // element (x=0, y=0, c=0, n=0)
     int S, C, N;
     long nstride;                // floats between frames
-    int boxx, boxy;              // box = boxx x boxy x C x 1
+    int boxx, boxy, boxc;        // box = boxx x boxy x boxc x 1
 };
 struct WgradTmaArgs {
     CUtensorMap tm_in, tm_g;
     TmaView vin, vg;
     int Cin, Cout, S, N, R, strips;
+    int Cc, Oc, csets;           // channels per CTA: blockIdx.y = oset * csets + cset owns ci in [cset*Cc, +Cc) x co in [oset*Oc, +Oc)
     int in_plane, g_plane;       // boxx * boxy of each view
     int stage_floats, g_off;     // per stage; offset of g inside a stage
     int stages;                  // 2..4 strips in flight (as many as fit next to the fold buffer)
     float* partials;
 };
 
-__device__ __forceinline__ void tma_box_load(float* dst, const CUtensorMap* tm, const TmaView& v, int x, int y, int n,
-                                             unsigned long long* bar) {
+__device__ __forceinline__ void tma_box_load(float* dst, const CUtensorMap* tm, const TmaView& v, int x, int y, int c0,
+                                             int n, unsigned long long* bar) {
 #ifdef PAIG_EMU
     (void)tm; (void)bar;
-    for (int c = 0; c < v.C; ++c)
+    for (int c = 0; c < v.boxc; ++c)
         for (int r = 0; r < v.boxy; ++r)
             for (int k = 0; k < v.boxx; ++k) {
                 const int gx = x + k, gy = y + r;
                 float val = 0.f;
-                if (gx >= 0 && gx < v.S && gy >= 0 && gy < v.S && n < v.N)
-                    val = v.base[(long)n * v.nstride + ((long)c * v.S + gy) * v.S + gx];
+                if (gx >= 0 && gx < v.S && gy >= 0 && gy < v.S && n < v.N && c0 + c < v.C)
+                    val = v.base[(long)n * v.nstride + ((long)(c0 + c) * v.S + gy) * v.S + gx];
                 dst[(c * v.boxy + r) * v.boxx + k] = val;
             }
 #else
     const unsigned dst_a = (unsigned)__cvta_generic_to_shared(dst);
     const unsigned bar_a = (unsigned)__cvta_generic_to_shared(bar);
-    const int c0 = 0;
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
         ::"r"(dst_a), "l"(reinterpret_cast<uint64_t>(tm)), "r"(x), "r"(y), "r"(c0), "r"(n), "r"(bar_a)
@@ -93,15 +93,14 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
 #endif
     const int S = a.S, QX = (S + 3) / 4, R = a.R, kWtStages = a.stages;
     const int tid = threadIdx.x;
-    const int cob_n = (a.Cout + COB - 1) / COB;
-    const int G = cob_n * a.Cin;                                      // owner groups
-    const int gsets = gridDim.y;
-    const int G_per = (G + gsets - 1) / gsets;
+    // this CTA's channel block (layers too wide for one CTA's shared memory / 256 owner threads are split over grid.y)
+    const int Cc = a.Cc, Oc = a.Oc;
+    const int c_base = ((int)blockIdx.y % a.csets) * Cc, o_base = ((int)blockIdx.y / a.csets) * Oc;
+    const int G_per = (Oc / COB) * Cc;                                // owner groups (<= kWtThreads, host)
     const int P = max(1, kWtThreads / G_per);                         // pixel partitions
     const int grp_local = tid % G_per, part = tid / G_per;
-    const int grp = blockIdx.y * G_per + grp_local;
-    const bool owner = part < P && grp < G;
-    const int ci = owner ? grp % a.Cin : 0, cob = owner ? grp / a.Cin : 0;
+    const bool owner = part < P;
+    const int ci = owner ? grp_local % Cc : 0, cob = owner ? grp_local / Cc : 0;   // local to the channel block
 
     float acc[COB][9], bacc[COB];
 #pragma unroll
@@ -112,7 +111,7 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
     }
     const int items = a.N * a.strips;
     const int n_my = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const unsigned stage_bytes = (unsigned)((a.Cin * a.in_plane + a.Cout * a.g_plane) * sizeof(float));
+    const unsigned stage_bytes = (unsigned)((Cc * a.in_plane + Oc * a.g_plane) * sizeof(float));
 #ifndef PAIG_EMU
     if (tid == 0) {
         for (int s = 0; s < kWtMaxStages; ++s)
@@ -130,8 +129,8 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(stage_bytes) : "memory");
 #endif
-        tma_box_load(st, &a.tm_in, a.vin, -4, y0 - 1, f, &full[k % kWtStages]);
-        tma_box_load(st + a.g_off, &a.tm_g, a.vg, 0, y0, f, &full[k % kWtStages]);
+        tma_box_load(st, &a.tm_in, a.vin, -4, y0 - 1, c_base, f, &full[k % kWtStages]);
+        tma_box_load(st + a.g_off, &a.tm_g, a.vg, 0, y0, o_base, f, &full[k % kWtStages]);
     };
     if (tid == 0)
         for (int k = 0; k < kWtStages && k < n_my; ++k) issue(k);
@@ -208,17 +207,15 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
     float* out = a.partials + (size_t)blockIdx.x * (nW + a.Cout);
     for (int e = tid; e < G_per * kRed; e += kWtThreads) {
         const int k = e % kRed, gl = e / kRed;
-        const int gg = blockIdx.y * G_per + gl;
-        if (gg >= G) continue;
         float s = 0.f;
         for (int p = 0; p < P; ++p) s += sRed[((size_t)p * G_per + gl) * kRed + k];
-        const int gci = gg % a.Cin, gcob = gg / a.Cin;
+        const int gci = c_base + gl % Cc, gcob = gl / Cc;
         if (k < COB * 9) {
-            const int co = gcob * COB + k / 9;
-            if (co < a.Cout) out[((size_t)co * a.Cin + gci) * 9 + (k % 9)] = s;
+            const int co = o_base + gcob * COB + k / 9;
+            out[((size_t)co * a.Cin + gci) * 9 + (k % 9)] = s;
         } else if (gci == 0) {
-            const int co = gcob * COB + (k - COB * 9);
-            if (co < a.Cout) out[nW + co] = s;
+            const int co = o_base + gcob * COB + (k - COB * 9);
+            out[nW + co] = s;
         }
     }
 }
@@ -264,7 +261,7 @@ bool make_map(CUtensorMap* tm, const TmaView& v) {
     if (!fn) return false;
     const cuuint64_t dims[4] = {(cuuint64_t)v.S, (cuuint64_t)v.S, (cuuint64_t)v.C, (cuuint64_t)v.N};
     const cuuint64_t strides[3] = {(cuuint64_t)v.S * 4, (cuuint64_t)v.S * v.S * 4, (cuuint64_t)v.nstride * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)v.boxx, (cuuint32_t)v.boxy, (cuuint32_t)v.C, 1};
+    const cuuint32_t box[4] = {(cuuint32_t)v.boxx, (cuuint32_t)v.boxy, (cuuint32_t)v.boxc, 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)v.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -290,54 +287,67 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
     // fewer barrier round trips and less halo re-read.
     static const int forced_R = getenv("PAIG_WGRAD_R") ? atoi(getenv("PAIG_WGRAD_R")) : 0;
     const size_t budget = (110 * 1024 - 128) / sizeof(float);
+    const int COB = (a.Cout % 8) == 0 ? 8 : 4;
+    if (a.Cout % COB) return -1;
     const int cands[7] = {(S + 1) | 1, 13, 11, 9, 7, 5, 3};
     bool found = false;
-    double best_cost = 0;
     WgradTmaArgs best = a;
-    for (int ci = 0; ci < 7; ++ci) {
-        const int R = forced_R > 0 ? forced_R : cands[ci];
-        if (R > ((S + 1) | 1) || (R & 1) == 0) continue;
-        WgradTmaArgs c = a;
-        c.R = R;
-        c.strips = cdiv(S, R);
-        c.vin = TmaView{w.in, S, w.Cin, w.N, w.in_bs, pick_boxx(S + 5, R + 2), R + 2};    // image columns -4 .. S
-        c.vg = TmaView{w.g, S, w.Cout, w.N, w.g_bs, pick_boxx(S, R), R};
-        if (c.vin.boxx < 0 || c.vg.boxx < 0 || c.vin.boxx > 256 || c.vg.boxx > 256 || R + 2 > 256) continue;
-        c.in_plane = c.vin.boxx * c.vin.boxy;
-        c.g_plane = c.vg.boxx * c.vg.boxy;
-        c.g_off = (c.Cin * c.in_plane + 31) & ~31;                     // 128-byte aligned TMA destinations
-        c.stage_floats = (c.g_off + c.Cout * c.g_plane + 31) & ~31;
-        c.stages = (int)(budget / c.stage_floats);
-        if (c.stages > kWtMaxStages) c.stages = kWtMaxStages;
-        if (c.stages < 2) continue;                                    // two CTAs per SM, two strips in flight
-        // rows fetched per frame (halo re-reads + padding of the last strip) plus a fixed cost per strip
-        const double cost = (double)c.strips * (R + 2) + 3.0 * c.strips;
-        if (!found || cost < best_cost) { found = true; best_cost = cost; best = c; }
-        if (forced_R > 0) break;
+    // Channel blocks: the fewest CTAs-per-strip (csets x osets) whose stage fits twice next to a second CTA and whose
+    // owner groups fit the 256 threads; ties prefer splitting the input channels (their planes carry the halo).
+    for (int sets = 1; sets <= 64 && !found; ++sets) {
+        for (int osets = 1; osets <= sets && !found; ++osets) {
+            if (sets % osets) continue;
+            const int csets = sets / osets;
+            if (a.Cin % csets || a.Cout % osets) continue;
+            const int Cc = a.Cin / csets, Oc = a.Cout / osets;
+            if (Oc % COB || (Oc / COB) * Cc > kWtThreads || Cc > 256 || Oc > 256) continue;
+            double best_cost = 0;
+            for (int ci = 0; ci < 7; ++ci) {
+                const int R = forced_R > 0 ? forced_R : cands[ci];
+                if (R > ((S + 1) | 1) || (R & 1) == 0) continue;
+                WgradTmaArgs c = a;
+                c.R = R;
+                c.strips = cdiv(S, R);
+                c.Cc = Cc; c.Oc = Oc; c.csets = csets;
+                c.vin = TmaView{w.in, S, w.Cin, w.N, w.in_bs, pick_boxx(S + 5, R + 2), R + 2, Cc};    // image columns -4 .. S
+                c.vg = TmaView{w.g, S, w.Cout, w.N, w.g_bs, pick_boxx(S, R), R, Oc};
+                if (c.vin.boxx < 0 || c.vg.boxx < 0 || c.vin.boxx > 256 || c.vg.boxx > 256 || R + 2 > 256) continue;
+                c.in_plane = c.vin.boxx * c.vin.boxy;
+                c.g_plane = c.vg.boxx * c.vg.boxy;
+                c.g_off = (Cc * c.in_plane + 31) & ~31;                    // 128-byte aligned TMA destinations
+                c.stage_floats = (c.g_off + Oc * c.g_plane + 31) & ~31;
+                c.stages = (int)(budget / c.stage_floats);
+                if (c.stages > kWtMaxStages) c.stages = kWtMaxStages;
+                if (c.stages < 2) continue;                                // two CTAs per SM, two strips in flight
+                // rows fetched per frame (halo re-reads + padding of the last strip) plus a fixed cost per strip
+                const double cost = (double)c.strips * (R + 2) + 3.0 * c.strips;
+                if (!found || cost < best_cost) { found = true; best_cost = cost; best = c; }
+                if (forced_R > 0) break;
+            }
+        }
     }
     if (!found) return -1;
     a = best;
-    const int COB = (a.Cout % 8) == 0 ? 8 : 4;
-    if (a.Cout % COB) return -1;
-    const int G = ((a.Cout + COB - 1) / COB) * a.Cin;
-    const int gsets = cdiv(G, kWtThreads);
-    const int G_per = cdiv(G, gsets);
+    const int sets = a.csets * (a.Cout / a.Oc);
+    const int G_per = (a.Oc / COB) * a.Cc;
     const int P = kWtThreads / G_per > 0 ? kWtThreads / G_per : 1;
     const size_t red = (size_t)P * G_per * COB * 10;
     const size_t tile = (size_t)a.stages * a.stage_floats;
     const size_t smem = (tile > red ? tile : red) * sizeof(float) + 128;
     if (smem > 110 * 1024) return -1;
     if (!make_map(&a.tm_in, a.vin) || !make_map(&a.tm_g, a.vg)) return -1;
+    // one resident wave: 296 CTAs shared between the channel blocks; every CTA column writes one partial
     int ctas = a.N * a.strips;
-    if (ctas > kWgradMaxCtas) ctas = kWgradMaxCtas;
+    const int cap = kWgradMaxCtas / sets > 0 ? kWgradMaxCtas / sets : 1;
+    if (ctas > cap) ctas = cap;
     static const bool debug = getenv("PAIG_DEBUG") != nullptr;
     if (debug)
-        fprintf(stderr, "[paig] wgrad_tma %d->%d S=%d N=%d R=%d strips=%d stages=%d in box %dx%d g box %dx%d stage=%d floats smem=%zu ctas=%d gsets=%d\n",
+        fprintf(stderr, "[paig] wgrad_tma %d->%d S=%d N=%d R=%d strips=%d stages=%d in box %dx%d g box %dx%d stage=%d floats smem=%zu ctas=%d blocks=%dx%d (Cc=%d Oc=%d)\n",
                 a.Cin, a.Cout, S, a.N, a.R, a.strips, a.stages, a.vin.boxx, a.vin.boxy, a.vg.boxx, a.vg.boxy, a.stage_floats, smem, ctas,
-                gsets);
-    if (COB == 8) launch(conv3x3_wgrad_tma_kernel<8>, dim3(ctas, gsets), dim3(kWtThreads), smem, st, a);
-    else launch(conv3x3_wgrad_tma_kernel<4>, dim3(ctas, gsets), dim3(kWtThreads), smem, st, a);
-    int rc = check_launch("conv3x3_wgrad");
+                a.csets, sets / a.csets, a.Cc, a.Oc);
+    if (COB == 8) launch(conv3x3_wgrad_tma_kernel<8>, dim3(ctas, sets), dim3(kWtThreads), smem, st, a);
+    else launch(conv3x3_wgrad_tma_kernel<4>, dim3(ctas, sets), dim3(kWtThreads), smem, st, a);
+    int rc = check_launch(layer_name("conv3x3_wgrad", -a.Cin, a.Cout, a.S));   // (negative Cin marks the TMA kernel)
     if (rc) return rc;
     const int nW = a.Cout * a.Cin * 9;
     if (w.defer) return w.defer->add(a.partials, ctas, nW + a.Cout, nW, dW, a.Cout, db) ? 0 : 1;
