@@ -29,6 +29,9 @@ namespace paig {
 
 constexpr int kFusedThreads = 512;
 constexpr int kFusedMaxOps = 24;
+// The weight prefetch (proxy fence + expect_tx + bulk copy, several hundred cycles) is issued by the last warp: ops
+// with fewer than 512 thread tiles leave it idle, so the cost leaves the critical path of warp 0.
+constexpr int kIssueThread = kFusedThreads - 32;
 constexpr size_t kFusedSmemLimit = 227 * 1024 - 4096;   // dynamic part; the op table and barriers are static
 
 enum { F_CONV = 0, F_POOL = 1, F_HEAD = 2, F_UPT = 3, F_POOLT = 4, F_HEADT = 5 };
@@ -182,10 +185,32 @@ __device__ __forceinline__ void conv_epilogue(const float (&acc)[PY][CO][4], con
                                               const float* bias, int cg, int y0, int qx, int f) {
     const int S = g.S, x0 = 4 * qx;
     const bool vec = (S & 3) == 0;
+    // ReLU adjoint gates: four channel rows' gate loads go out before the first of their stores (the stores may alias
+    // them as far as the compiler knows, which would serialise one L2 round trip per output channel)
+    constexpr int KB = PY * CO > 32 ? 1 : 4;      // (64-accumulator tiles have no registers to spare)
 #pragma unroll
     for (int r = 0; r < PY; ++r)
 #pragma unroll
-    for (int c = 0; c < CO; ++c) {
+    for (int c0 = 0; c0 < CO; c0 += KB) {
+    float4 gate[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        gate[k] = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (op.gmask) {
+            const float* m = op.gmask + (long)f * op.gmask_bs + ((long)(cg * CO + c0 + k) * S + y0 + r) * S + x0;
+            if (vec) {
+                gate[k] = *reinterpret_cast<const float4*>(m);
+            } else {
+                gate[k].x = m[0];
+                if (x0 + 1 < S) gate[k].y = m[1];
+                if (x0 + 2 < S) gate[k].z = m[2];
+                if (x0 + 3 < S) gate[k].w = m[3];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        const int c = c0 + k;
         const int co = cg * CO + c, y = y0 + r;
         const float b = op.bias ? bias[co] : 0.f;
         float o[4];
@@ -194,17 +219,10 @@ __device__ __forceinline__ void conv_epilogue(const float (&acc)[PY][CO][4], con
             o[p] = acc[r][c][p] + b;
             if (op.relu) o[p] = fmaxf(o[p], 0.f);
         }
-        if (op.gmask) {                       // ReLU adjoint: pass the gradient where the forward activation was positive
-            const float* m = op.gmask + (long)f * op.gmask_bs + ((long)co * S + y) * S + x0;
-            if (vec) {
-                const float4 m4 = *reinterpret_cast<const float4*>(m);
-                o[0] = m4.x > 0.f ? o[0] : 0.f; o[1] = m4.y > 0.f ? o[1] : 0.f;
-                o[2] = m4.z > 0.f ? o[2] : 0.f; o[3] = m4.w > 0.f ? o[3] : 0.f;
-            } else {
-#pragma unroll
-                for (int p = 0; p < 4; ++p)
-                    if (x0 + p < S) o[p] = m[p] > 0.f ? o[p] : 0.f;
-            }
+        {                                     // pass the gradient where the forward activation was positive
+            const float4 m4 = gate[k];
+            o[0] = m4.x > 0.f ? o[0] : 0.f; o[1] = m4.y > 0.f ? o[1] : 0.f;
+            o[2] = m4.z > 0.f ? o[2] : 0.f; o[3] = m4.w > 0.f ? o[3] : 0.f;
         }
         if (op.out >= 0) {
             float* d = sm + op.out + co * g.plane + (y + 1) * g.P + x0 + 1;
@@ -222,6 +240,7 @@ __device__ __forceinline__ void conv_epilogue(const float (&acc)[PY][CO][4], con
                     if (x0 + p < S) d[p] = o[p];
             }
         }
+    }
     }
 }
 
@@ -363,14 +382,11 @@ __device__ __forceinline__ void run_conv(const FusedOp& op, float* sm, int f, in
 
 template <int COUT>
 __device__ __forceinline__ void run_conv_co(const FusedOp& op, float* sm, int f, int tid, long long* tm) {
-    if (op.py_tile == 2) {
-        if (op.co_tile == 8) run_conv<8, COUT, 2>(op, sm, f, tid, tm);
-        else run_conv<4, COUT, 2>(op, sm, f, tid, tm);
-    } else {
-        if (COUT >= 16 && op.co_tile == 16) run_conv<(COUT >= 16 ? 16 : 4), COUT, 1>(op, sm, f, tid, tm);
-        else if (op.co_tile == 8) run_conv<8, COUT, 1>(op, sm, f, tid, tm);
-        else run_conv<4, COUT, 1>(op, sm, f, tid, tm);
-    }
+    // (8 x 2 tiles were measured too: never the fastest; 16 x 1 stays for the single-pass upsampling convs at 36 px)
+    if (op.py_tile == 2) run_conv<4, COUT, 2>(op, sm, f, tid, tm);
+    else if (COUT >= 16 && op.co_tile == 16) run_conv<(COUT >= 16 ? 16 : 4), COUT, 1>(op, sm, f, tid, tm);
+    else if (op.co_tile == 8) run_conv<8, COUT, 1>(op, sm, f, tid, tm);
+    else run_conv<4, COUT, 1>(op, sm, f, tid, tm);
 }
 
 __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const FusedPlan P) {
@@ -395,7 +411,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const 
     const Geo gx = geo_of(P.H);
     const int HW = P.H * P.H;
     for (int f = blockIdx.x; f < P.N; f += gridDim.x) {
-        if (tid == 0 && P.first_w >= 0) {
+        if (tid == kIssueThread && P.first_w >= 0) {
             const FusedOp& o = s_ops[P.first_w];
             bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
         }
@@ -423,7 +439,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const 
 #endif
         for (int t = 0; t < P.nops; ++t) {
             const FusedOp op = s_ops[t];
-            if (tid == 0 && op.next_w >= 0) {
+            if (tid == kIssueThread && op.next_w >= 0) {
                 const FusedOp& o = s_ops[op.next_w];
                 bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
             }
@@ -655,7 +671,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_bwd_kernel(const 
     __syncthreads();
     unsigned phase0 = 0, phase1 = 0;
     for (int f = blockIdx.x; f < P.N; f += gridDim.x) {
-        if (tid == 0 && P.first_w >= 0) {
+        if (tid == kIssueThread && P.first_w >= 0) {
             const FusedOp& o = s_ops[P.first_w];
             bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
         }
@@ -664,7 +680,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_bwd_kernel(const 
 #endif
         for (int t = 0; t < P.nops; ++t) {
             const FusedOp op = s_ops[t];
-            if (tid == 0 && op.next_w >= 0) {
+            if (tid == kIssueThread && op.next_w >= 0) {
                 const FusedOp& o = s_ops[op.next_w];
                 bulk_issue(sm + o.wsm, P.wpack + o.wglob, (unsigned)o.wfloats * 4u, &bars[o.wbar]);
             }
@@ -797,7 +813,7 @@ bool choose_tile(FusedOp& fo, bool single_pass) {
     for (int py = 1; py <= 2; ++py) {
         if (fo.S % py) continue;
         for (int co = 4; co <= 16; co *= 2) {
-            if (fo.Cout % co || (py == 2 && co == 16)) continue;
+            if (fo.Cout % co || (py == 2 && co >= 8)) continue;
             const int items = (fo.S / py) * g.nqx * (fo.Cout / co);
             const int passes = (items + kFusedThreads - 1) / kFusedThreads;
             if (single_pass && passes > 1) continue;

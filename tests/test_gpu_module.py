@@ -227,3 +227,23 @@ def test_staged_host_input_step_equals_device_step():
         # bit-identical: every reduction of the step runs in a fixed order (the decoder gathers template gradients
         # instead of scattering them with float atomics)
         assert torch.equal(net.flat_gradients().detach().cpu()[:-4], want[slot][1][:-4])
+
+
+@pytest.mark.parametrize("task,max_launches", [("spring_color", 50), ("bouncing_balls", 50), ("3bp_color", 60)])
+def test_fused_unet_kernels_are_the_path_taken(task, max_launches):
+    """The ShallowUNet tasks must run the persistent fused forward / backward-data kernels, not the per-layer kernels
+    they fall back to when a plan does not fit on chip (a silent fallback costs 2x and changes nothing else): the
+    library's own launch counter bounds the launches of one LIVE training step."""
+    from paig_reproduction_b200 import _lib
+    lib = _lib.load()
+    spec = po.TASKS[task]
+    net = _net(task, spec.seq_len, 3.0)
+    net.load_state_dict(po.init_state_dict(spec, 0), strict=True)
+    x = po.synthetic_frames(spec, 100, spec.seq_len, 5).to(DEV)
+    net.train_step(x)
+    torch.cuda.synchronize()
+    n0 = lib.paig_launch_count()
+    net.train_step(x)
+    torch.cuda.synchronize()
+    n = lib.paig_launch_count() - n0
+    assert 0 < n <= max_launches, "%d launches in one %s step" % (n, task)
