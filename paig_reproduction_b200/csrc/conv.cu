@@ -12,6 +12,7 @@
 #include "internal.h"
 
 #include <cstdint>
+#include <cstdlib>
 
 namespace paig {
 
@@ -60,19 +61,46 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ sDst, int plane, 
             }
         }
     } else {
-        const int rowlen = S;
-        const int total = nfr * nc * RT * rowlen;
-        for (int e = tid; e < total; e += nthr) {
-            const int col = e % rowlen, R = e / rowlen;
-            const int r = R % RT, t = R / RT, ci = t % nc, ff = t / nc;
-            const int gy = y0 + r + yofs, gf = f0 + ff;
-            float v = 0.f;
-            if (gf < N && (unsigned)gy < (unsigned)S) {
-                const long off = ((long)(cbase + ci) * S + gy) * S + col;
-                v = src[(long)gf * src_bs + off];
-                if (msk && !(msk[(long)gf * msk_bs + off] > 0.f)) v = 0.f;
+        // generic (S = 18, 9, 36 ...): a warp stages one row at a time -- the (frame, channel, row) decomposition is
+        // done once per row instead of once per element, and the lanes read the row coalesced
+        const int lane = tid & 31;
+        const int rows_total = nfr * nc * RT;
+        const int nw = nthr >> 5;
+        constexpr int U = 8;                                  // rows in flight per warp: the loads are latency-bound
+        for (int R0 = tid >> 5; R0 < rows_total; R0 += U * nw) {
+            float v[U][2];
+            float* d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int R = R0 + u * nw;
+                v[u][0] = v[u][1] = 0.f;
+                d[u] = nullptr;
+                if (R < rows_total) {
+                    const int r = R % RT, t = R / RT, ci = t % nc, ff = t / nc;
+                    const int gy = y0 + r + yofs, gf = f0 + ff;
+                    d[u] = sDst + (ff * cslots + ci) * plane + r * PITCH + col0;
+                    if (gf < N && (unsigned)gy < (unsigned)S) {
+                        const long off = ((long)(cbase + ci) * S + gy) * S;
+                        const float* sp = src + (long)gf * src_bs + off;
+                        const float* mp = msk ? msk + (long)gf * msk_bs + off : nullptr;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int col = lane + 32 * h;
+                            if (col < S) {
+                                float x = sp[col];
+                                if (mp && !(mp[col] > 0.f)) x = 0.f;
+                                v[u][h] = x;
+                            }
+                        }
+                    }
+                }
             }
-            sDst[(ff * cslots + ci) * plane + r * PITCH + col0 + col] = v;
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (d[u]) {
+                    if (lane < S) d[u][lane] = v[u][0];
+                    if (lane + 32 < S) d[u][lane + 32] = v[u][1];
+                }
         }
     }
 }
@@ -84,6 +112,29 @@ __device__ __forceinline__ void zero_halo_cols(float* sDst, int rows_total, int 
         const int row = e / hc, k = e % hc;
         sDst[row * PITCH + (k == 0 ? 0 : S + k)] = 0.f;
     }
+}
+
+// Asynchronous variant of the generic row staging (no ReLU mask): every element is one 4-byte cp.async (LDGSTS) into
+// the same zero-haloed tile, rows outside the image are zero-filled through the src-size operand, nothing waits here.
+// Used by the weight-gradient kernel to stage strip k+1 while strip k is multiplied (18- and 9-px levels of 3bp, whose
+// 72- and 36-byte row pitch the TMA unit cannot address).
+__device__ __forceinline__ void stage_rows_async(float* sDst, int plane, int PITCH, int RT, int nc, const float* src,
+                                                 long src_bs, int f, int y0, int S, int tid, int nthr, int col0, int yofs) {
+#ifndef PAIG_EMU
+    const int lane = tid & 31;
+    const int rows_total = nc * RT;
+    for (int R = tid >> 5; R < rows_total; R += nthr >> 5) {
+        const int r = R % RT, ci = R / RT;
+        const int gy = y0 + r + yofs;
+        const bool ok = (unsigned)gy < (unsigned)S;
+        const float* sp = src + (long)f * src_bs + ((long)ci * S + (ok ? gy : 0)) * S;
+        const unsigned d0 = (unsigned)__cvta_generic_to_shared(sDst + ci * plane + r * PITCH + col0);
+        const unsigned nbytes = ok ? 4u : 0u;
+        for (int col = lane; col < S; col += 32)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * col), "l"(sp + col), "r"(nbytes)
+                         : "memory");
+    }
+#endif
 }
 
 template <int CO_T, int LOG_QX>
@@ -238,7 +289,7 @@ int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
 // walks; pixel partitions are folded through shared memory at the end and each CTA leaves one partial.
 //   dW[co,ci,ky,kx] = sum_{n,y,x} g[n,co,y,x] * in[n,ci,y+ky-1,x+kx-1],   g = dOut * (act > 0)
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kWgTH = 8;                  // rows per staged strip
+constexpr int kWgTH = 8;                  // rows per staged strip (default; small images are staged whole, WgradArgs::TH)
 
 template <int LOG_QX>
 __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a) {
@@ -246,8 +297,9 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
     const int S = a.S, QX = (S + 3) / 4;
     const int PITCH = 4 * QX + 4;
     const int in_plane = a.in_plane, g_plane = a.g_plane;            // padded to == 4 (mod 32) floats
-    float* sIn = smem;                                                // [Cin][kWgTH+2][PITCH]
-    float* sG = smem + (size_t)a.Cin * in_plane;                      // [Cout][kWgTH][PITCH-4 .. ] pitch 4*QX
+    const int TH = a.TH;                                              // rows per staged strip
+    float* sIn = smem;                                                // [Cin][TH+2][PITCH]
+    float* sG = smem + (size_t)a.Cin * in_plane;                      // [Cout][TH][PITCH-4 .. ] pitch 4*QX
     const int GP = 4 * QX;
     const int tid = threadIdx.x;
     const int cob_n = (a.Cout + 3) / 4;
@@ -268,24 +320,54 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
 #pragma unroll
         for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
     }
-    // halo columns / plane padding are never written by the row staging: clear the tile once
-    for (int e = tid; e < a.Cin * in_plane + a.Cout * g_plane; e += kConvThreads) smem[e] = 0.f;
+    // halo columns / plane padding are never written by the row staging: clear the tile(s) once
+    const int stage_floats = a.Cin * in_plane + a.Cout * g_plane;
+    const bool async = LOG_QX < 0 && a.async2;                         // two stage buffers, cp.async staging (host)
+    for (int e = tid; e < (async ? 2 : 1) * stage_floats; e += kConvThreads) smem[e] = 0.f;
     __syncthreads();
-    const int strips = (S + kWgTH - 1) / kWgTH;
+    const int strips = (S + TH - 1) / TH;
     const int items = a.N * strips;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int f = item / strips, y0 = (item % strips) * kWgTH;
-        const int rows = min(kWgTH, S - y0);
-        // ---- stage input strip (zero halo) and the masked output-gradient strip ----
-        stage_rows<LOG_QX>(sIn, in_plane, 0, PITCH, kWgTH + 2, 1, a.Cin, a.in, a.in_bs, a.in_mask, a.in_mask_bs, 0, f, a.N,
-                           y0, S, tid, kConvThreads);
-        stage_rows<LOG_QX>(sG, g_plane, 0, GP, kWgTH, 1, a.Cout, a.g, a.g_bs, a.act, a.act_bs, 0, f, a.N, y0, S, tid,
-                           kConvThreads, 0, 0);
+    auto issue = [&](int item, int buf) {                              // cp.async staging of one strip (no masks)
+        const int f = item / strips, y0 = (item % strips) * TH;
+        float* b = smem + buf * stage_floats;
+        stage_rows_async(b, in_plane, PITCH, TH + 2, a.Cin, a.in, a.in_bs, f, y0, S, tid, kConvThreads, 1, -1);
+        stage_rows_async(b + (size_t)a.Cin * in_plane, g_plane, GP, TH, a.Cout, a.g, a.g_bs, f, y0, S, tid, kConvThreads, 0, 0);
+#ifndef PAIG_EMU
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
+    };
+    if (async && (int)blockIdx.x < items) issue(blockIdx.x, 0);
+    int kbuf = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x, kbuf ^= 1) {
+        const int f = item / strips, y0 = (item % strips) * TH;
+        const int rows = min(TH, S - y0);
+        if (async) {
+            // strip k+1 goes out before strip k is waited for; the barrier at the end of the previous trip freed its buffer
+            sIn = smem + kbuf * stage_floats;
+            sG = sIn + (size_t)a.Cin * in_plane;
+#ifndef PAIG_EMU
+            if (item + (int)gridDim.x < items) {
+                issue(item + gridDim.x, kbuf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+#endif
+        } else {
+            // ---- stage input strip (zero halo) and the masked output-gradient strip ----
+            stage_rows<LOG_QX>(sIn, in_plane, 0, PITCH, TH + 2, 1, a.Cin, a.in, a.in_bs, a.in_mask, a.in_mask_bs, 0, f, a.N,
+                               y0, S, tid, kConvThreads);
+            stage_rows<LOG_QX>(sG, g_plane, 0, GP, TH, 1, a.Cout, a.g, a.g_bs, a.act, a.act_bs, 0, f, a.N, y0, S, tid,
+                               kConvThreads, 0, 0);
+        }
         __syncthreads();
         if (owner) {
             const int nq = rows * QX;
+            // quads q = part, part + P, ...: (row, quad-in-row) advance without a division per step
+            const int dr = P / QX, dq = P % QX;
+            int r = part / QX, qxx = part % QX;
             for (int q = part; q < nq; q += P) {
-                const int r = q / QX, x0 = (q % QX) * 4;
+                const int x0 = qxx * 4;
                 float v[3][6];
                 const float* ip = sIn + ci * in_plane + r * PITCH + x0;
 #pragma unroll
@@ -309,6 +391,8 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
                                 for (int p = 0; p < 4; ++p) acc[c][ky * 3 + kx] += gv[p] * v[ky][kx + p];
                     }
                 }
+                r += dr; qxx += dq;
+                if (qxx >= QX) { qxx -= QX; ++r; }
             }
         }
         __syncthreads();
@@ -436,20 +520,34 @@ int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t s
         if (rc >= 0) return rc;
     }
     const int QX = (a.S + 3) / 4, PITCH = 4 * QX + 4;
-    a.in_plane = pad_plane((kWgTH + 2) * PITCH);
-    a.g_plane = pad_plane(kWgTH * 4 * QX);
+    // images up to 20 px are staged whole (18 px in strips of 8 would leave a 2-row strip paying a full stage + two
+    // barriers) as long as two CTAs still fit an SM
+    a.TH = kWgTH;
+    if (a.S <= 20) a.TH = a.S <= 10 ? a.S : (a.S + 1) / 2;        // 18 px: two strips of 9, not 8 + 8 + 2
+    a.in_plane = pad_plane((a.TH + 2) * PITCH);
+    a.g_plane = pad_plane(a.TH * 4 * QX);
     const int G = ((a.Cout + 3) / 4) * a.Cin;
     const int gsets = cdiv(G, kConvThreads);
     const int G_per = cdiv(G, gsets);
     const int P = kConvThreads / G_per > 0 ? kConvThreads / G_per : 1;
-    const size_t tile = (size_t)a.Cin * a.in_plane + (size_t)a.Cout * a.g_plane;
+    size_t tile = (size_t)a.Cin * a.in_plane + (size_t)a.Cout * a.g_plane;
+    // rows the TMA unit cannot address (pitch not a multiple of 16 B): double-buffered cp.async staging when the tile
+    // fits twice next to a second CTA and no ReLU mask has to be applied on the way in
+    static const bool async_off = getenv("PAIG_WGRAD_SYNC") != nullptr;
+    a.async2 = 0;
+#ifndef PAIG_EMU
+    if (!async_off && a.S != 4 * QX && !a.in_mask && !a.act && 2 * tile * sizeof(float) <= 110 * 1024) {
+        a.async2 = 1;
+        tile *= 2;
+    }
+#endif
     const size_t red = (size_t)P * G_per * 40;
     const size_t smem = (tile > red ? tile : red) * sizeof(float);
     if (smem > 220 * 1024) {
         set_error("conv3x3_wgrad: %d->%d channels at %d px needs %zu B of shared memory", a.Cin, a.Cout, a.S, smem);
         return 1;
     }
-    const int strips = cdiv(a.S, kWgTH);
+    const int strips = cdiv(a.S, a.TH);
     int ctas = a.N * strips;
     if (ctas > kWgradMaxCtas) ctas = kWgradMaxCtas;
     int lq = -1;

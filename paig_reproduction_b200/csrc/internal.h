@@ -77,7 +77,7 @@ struct WgradArgs {
     int S = 0, N = 0;
     float* partials = nullptr;                                    // >= wgrad_partials_floats(Cin, Cout)
     ReduceBatch* defer = nullptr;                                 // queue the final fold instead of launching it
-    int in_plane = 0, g_plane = 0;                                // filled by conv3x3_wgrad()
+    int in_plane = 0, g_plane = 0, TH = 0, async2 = 0;            // filled by conv3x3_wgrad()
 };
 int conv3x3_wgrad(const WgradArgs& a, float* dW, float* db, cudaStream_t st);
 // wgrad_tma.cu: TMA-staged variant; -1 when the layer geometry does not qualify (then conv3x3_wgrad's own kernel runs)
