@@ -21,7 +21,7 @@ constexpr int kCK = 8;                 // input channels staged per pass
 
 // ---------------------------------------------------------------------------------------------------------
 // conv3x3: each thread produces 4 horizontally adjacent pixels x CO_T output channels.
-// Block = FPB frames x TH rows x QX quads (<= 256 threads); blockIdx = (frame group, row strip, cout group).
+// Block = FPB frames x TH rows x QX quads (<= 256 threads); blockIdx = (cout group, row strip, frame group).
 // ---------------------------------------------------------------------------------------------------------
 // Row-wise staging of NCHW rows into a zero-haloed shared tile (image column x sits at tile column x+1).
 // LOG_QX >= 0: S == 4 << LOG_QX and every pointer is 16-byte aligned, so a row is QX float4 loads and the
@@ -147,7 +147,9 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_kernel(ConvArgs a) {
     float* sW = smem + FPB * kCK * plane;                 // [kCK][9][CO_T]
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int qx = tid % QX, ty = (tid / QX) % TH, fb = tid / (QX * TH);
-    const int f0 = blockIdx.x * FPB, y0 = blockIdx.y * TH, co0 = blockIdx.z * CO_T;
+    // the output-channel group is the fastest grid dimension: the CTAs that re-read one input tile for different
+    // output channels run together and share it in L2 (with the batch fastest the second group found 1 % L2 hits)
+    const int f0 = blockIdx.z * FPB, y0 = blockIdx.y * TH, co0 = blockIdx.x * CO_T;
     const int y = y0 + ty, f = f0 + fb;
     const bool active = fb < FPB && f < a.N && y < S;
 
@@ -255,7 +257,7 @@ int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
     const bool wide = (a.Cout % 16) == 0;
     const int CO_T = wide ? 16 : 8;
     const size_t smem = ((size_t)a.FPB * kCK * (a.TH + 2) * PITCH + (size_t)kCK * 9 * CO_T) * sizeof(float);
-    dim3 grid(cdiv(a.N, a.FPB), strips, cdiv(a.Cout, CO_T));
+    dim3 grid(cdiv(a.Cout, CO_T), strips, cdiv(a.N, a.FPB));
     // vector staging needs S = 4 * 2^k and 16-byte aligned rows
     int lq = -1;
     const bool aligned = ((uintptr_t)a.in % 16 == 0) && (a.in_bs % 4 == 0) &&
