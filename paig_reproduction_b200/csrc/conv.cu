@@ -231,6 +231,141 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_kernel(ConvArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// The same convolution with the staging taken off the critical path (ncu on the kernel above, 64-px UNet: issue
+// slots 65 % busy, long_scoreboard the top real stall -- every chunk of 8 input channels is stage, barrier,
+// multiply, barrier).  Here chunk k+1 (input rows as 16-byte cp.async, weights as 4-byte cp.async) is in flight
+// into the other buffer while chunk k is multiplied.  The image sits at tile column x+4 so the copies are
+// 16-byte aligned; a thread reads its 6 pixels as 4 B + 16 B + 4 B (the TMA weight-gradient kernel's pattern).
+// Needs S = 4 * 2^k, 16-byte aligned rows and no ReLU mask on the way in (the per-layer backward gates g in place).
+// ---------------------------------------------------------------------------------------------------------
+template <int CO_T, int LOG_QX>
+__global__ void __launch_bounds__(kConvThreads) conv3x3_async_kernel(ConvArgs a) {
+#ifndef PAIG_EMU
+    PAIG_DYN_SMEM(float, smem);
+    constexpr int QX = 1 << LOG_QX;
+    const int S = a.S, TH = a.TH, FPB = a.FPB, CK = a.CK;
+    constexpr int PITCH = 4 * QX + 8;
+    const int RT = TH + 2;
+    const int plane = RT * PITCH;
+    const int in_fl = FPB * CK * plane, stage_fl = in_fl + CK * 9 * CO_T;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int qx = tid & (QX - 1), ty = (tid >> LOG_QX) % TH, fb = tid / (QX * TH);
+    const int f0 = blockIdx.z * FPB, y0 = blockIdx.y * TH, co0 = blockIdx.x * CO_T;
+    const int y = y0 + ty, f = f0 + fb;
+    const bool active = fb < FPB && f < a.N && y < S;
+
+    float acc[CO_T][4];
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[c][p] = 0.f;
+    for (int e = tid; e < 2 * stage_fl; e += nthr) smem[e] = 0.f;      // halo columns are never written by the copies
+    __syncthreads();
+
+    auto issue = [&](int c0, int buf) {
+        const int nc = min(CK, a.Cin - c0);
+        float* sIn = smem + buf * stage_fl;
+        float* sW = sIn + in_fl;
+        // input rows: item = (frame, channel, row, quad); (channel, frame) advance without a division per item
+        {
+            const int step = nthr >> LOG_QX;
+            int R = tid >> LOG_QX;
+            int r = R % RT, t = R / RT;
+            int ci = t % nc, ff = t / nc;
+            while (ff < FPB) {
+                const int gy = y0 + r - 1, gf = f0 + ff;
+                const bool ok = gf < a.N && (unsigned)gy < (unsigned)S;
+                const float* src = ok ? a.in + (long)gf * a.in_bs + ((long)(c0 + ci) * S + gy) * S + 4 * qx : a.in;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(sIn + (ff * CK + ci) * plane + r * PITCH + 4 + 4 * qx);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+                r += step;
+                while (r >= RT) {
+                    r -= RT;
+                    if (++ci == nc) { ci = 0; ++ff; }
+                }
+            }
+        }
+        // weights of this (cin chunk, cout group): sW[ci][tap][co]
+        for (int e = tid; e < nc * 9 * CO_T; e += nthr) {
+            const int co = e % CO_T, tap = (e / CO_T) % 9, ci = e / (9 * CO_T);
+            const bool ok = co0 + co < a.Cout;
+            const float* src = !ok ? a.w
+                               : (a.transposed ? a.w + ((long)(c0 + ci) * a.Cout + (co0 + co)) * 9 + (8 - tap)
+                                               : a.w + ((long)(co0 + co) * a.Cin + (c0 + ci)) * 9 + tap);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(sW + (ci * 9 + tap) * CO_T + co);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4u : 0u) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    issue(0, 0);
+    int buf = 0;
+    for (int c0 = 0; c0 < a.Cin; c0 += CK, buf ^= 1) {
+        const int nc = min(CK, a.Cin - c0);
+        if (c0 + CK < a.Cin) {
+            issue(c0 + CK, buf ^ 1);                   // the barrier that ended the previous trip freed that buffer
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float* sIn = smem + buf * stage_fl;
+        const float* sW = sIn + in_fl;
+        if (active) {
+            for (int ci = 0; ci < nc; ++ci) {
+                const float* row = sIn + (fb * CK + ci) * plane + ty * PITCH + 4 * qx;
+                float v[3][6];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float4 p4 = *reinterpret_cast<const float4*>(row + r * PITCH + 4);
+                    v[r][0] = row[r * PITCH + 3]; v[r][1] = p4.x; v[r][2] = p4.y; v[r][3] = p4.z; v[r][4] = p4.w;
+                    v[r][5] = row[r * PITCH + 8];
+                }
+                const float* wp = sW + ci * 9 * CO_T;
+#pragma unroll
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const float* w = wp + (ky * 3 + kx) * CO_T;
+#pragma unroll
+                        for (int c4 = 0; c4 < CO_T; c4 += 4) {
+                            const float4 w4 = *reinterpret_cast<const float4*>(w + c4);
+                            const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                                for (int p = 0; p < 4; ++p) acc[c4 + c][p] += wv[c] * v[ky][kx + p];
+                        }
+                    }
+            }
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+    const int x0 = 4 * qx;
+#pragma unroll
+    for (int c = 0; c < CO_T; ++c) {
+        const int co = co0 + c;
+        if (co >= a.Cout) break;
+        const float bias = a.b ? a.b[co] : 0.f;
+        float o[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            o[p] = acc[c][p] + bias;
+            if (a.relu) o[p] = fmaxf(o[p], 0.f);
+        }
+        float* dst = a.out + (long)f * a.out_bs + ((long)co * S + y) * S + x0;
+        if ((a.out_bs & 3) == 0 && ((uintptr_t)a.out & 15) == 0) {
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) dst[p] = o[p];
+        }
+    }
+#endif
+}
+
 static void conv_geometry(int S, int N, int* QX, int* TH, int* FPB, int* strips) {
     *QX = (S + 3) / 4;
     const int per_frame = *QX * S;
@@ -267,6 +402,32 @@ int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
             if (a.QX == (1 << k)) lq = k;
     }
     dim3 blk(threads);
+#ifndef PAIG_EMU
+    // double-buffered cp.async variant: largest channel chunk (8, then 4) whose two stages leave room for a second CTA
+    static const bool async_off = getenv("PAIG_CONV_SYNC") != nullptr;
+    if (!async_off && lq >= 2 && !a.mask && a.Cin >= 8) {      // (8-px layers: 16 frames per CTA, measured 3 % slower)
+        const int PITCHa = 4 * a.QX + 8;
+        for (int ck = 8; ck >= 4; ck >>= 1) {
+            const size_t stage = (size_t)a.FPB * ck * (a.TH + 2) * PITCHa + (size_t)ck * 9 * CO_T;
+            const size_t smem2 = 2 * stage * sizeof(float);
+            if (smem2 > 110 * 1024) continue;
+            a.CK = ck;
+#define PAIG_CONVA_CASE(LQ)                                                                       \
+    case LQ:                                                                                      \
+        if (wide) launch(conv3x3_async_kernel<16, LQ>, grid, blk, smem2, st, a);                  \
+        else launch(conv3x3_async_kernel<8, LQ>, grid, blk, smem2, st, a);                        \
+        break;
+            switch (lq) {
+                PAIG_CONVA_CASE(1)
+                PAIG_CONVA_CASE(2)
+                PAIG_CONVA_CASE(3)
+                PAIG_CONVA_CASE(4)
+            }
+#undef PAIG_CONVA_CASE
+            return check_launch(layer_name("conv3x3", a.Cin, a.Cout, a.S));
+        }
+    }
+#endif
 #define PAIG_CONV_CASE(LQ)                                                                  \
     case LQ:                                                                                \
         if (wide) launch(conv3x3_kernel<16, LQ>, grid, blk, smem, st, a);                   \

@@ -48,7 +48,7 @@ struct ConvArgs {
     float* out = nullptr; long out_bs = 0; int Cout = 0;
     int S = 0, N = 0;
     int relu = 0, transposed = 0;
-    int QX = 0, TH = 0, FPB = 0;                       // filled by conv3x3()
+    int QX = 0, TH = 0, FPB = 0, CK = 0;               // filled by conv3x3()
 };
 int conv3x3(const ConvArgs& a, cudaStream_t st);
 constexpr int kWgradMaxCtas = 296;
