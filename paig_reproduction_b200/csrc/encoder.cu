@@ -303,7 +303,7 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
             w.Cin = op.in.C;
             w.g = go.p; w.g_bs = go.bs; w.Cout = op.out.C;
             // gate the gradient once in place: the TMA weight-gradient kernel needs it pre-gated, and the data-gradient
-            // kernel's own gate below becomes idempotent
+            // kernel reads it without a mask (which also lets it take the cp.async double-buffered variant)
             if (op.relu && (rc = relu_gate(go.p, go.bs, o.p, o.bs, op.out.C, o.S, L.N, st))) return rc;
             w.act = nullptr;
             w.S = o.S; w.N = L.N; w.partials = partials;
@@ -312,7 +312,7 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
                 View gi = view_of(L, ws, op.in, true);
                 ConvArgs a;
                 a.in = go.p; a.in_bs = go.bs; a.Cin = op.out.C;
-                a.mask = op.relu ? o.p : nullptr; a.mask_bs = o.bs;
+                a.mask = nullptr; a.mask_bs = 0;
                 a.w = p->conv[op.layer].w; a.transposed = 1;
                 a.out = gi.p; a.out_bs = gi.bs; a.Cout = op.in.C;
                 a.S = o.S; a.N = L.N;
