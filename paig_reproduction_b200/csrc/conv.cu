@@ -746,9 +746,32 @@ __global__ void __launch_bounds__(256) relu_gate_kernel(float* __restrict__ g, l
     if (!(act[f * act_bs + r] > 0.f)) g[f * g_bs + r] = 0.f;
 }
 
+// 16 bytes per thread, the frame on grid.y (no division); g is only touched where some activation is not positive
+__global__ void __launch_bounds__(256) relu_gate_vec_kernel(float* __restrict__ g, long g_bs, const float* __restrict__ act,
+                                                            long act_bs, int per4) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per4) return;
+    const long f = blockIdx.y;
+    const float4 a = reinterpret_cast<const float4*>(act + f * act_bs)[i];
+    const bool zx = !(a.x > 0.f), zy = !(a.y > 0.f), zz = !(a.z > 0.f), zw = !(a.w > 0.f);
+    if (!(zx | zy | zz | zw)) return;
+    float4* gp = reinterpret_cast<float4*>(g + f * g_bs) + i;
+    float4 v = *gp;
+    if (zx) v.x = 0.f;
+    if (zy) v.y = 0.f;
+    if (zz) v.z = 0.f;
+    if (zw) v.w = 0.f;
+    *gp = v;
+}
+
 int relu_gate(float* g, long g_bs, const float* act, long act_bs, int C, int S, int N, cudaStream_t st) {
     const long per = (long)C * S * S, total = per * N;
     if (total <= 0) return 0;
+    if (per % 4 == 0 && g_bs % 4 == 0 && act_bs % 4 == 0 && ((uintptr_t)g % 16) == 0 && ((uintptr_t)act % 16) == 0 &&
+        N <= 65535) {
+        launch(relu_gate_vec_kernel, dim3(cdiv(per / 4, 256), N), dim3(256), 0, st, g, g_bs, act, act_bs, (int)(per / 4));
+        return check_launch("relu_gate");
+    }
     launch(relu_gate_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, g, g_bs, act, act_bs, per, total);
     return check_launch("relu_gate");
 }
