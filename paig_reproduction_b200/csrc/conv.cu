@@ -121,16 +121,20 @@ __device__ __forceinline__ void zero_halo_cols(float* sDst, int rows_total, int 
 __device__ __forceinline__ void stage_rows_async(float* sDst, int plane, int PITCH, int RT, int nc, const float* src,
                                                  long src_bs, int f, int y0, int S, int tid, int nthr, int col0, int yofs) {
 #ifndef PAIG_EMU
-    const int lane = tid & 31;
+    // one row per thread: the (channel, row) decomposition and the address set-up cost ~40 instructions, the S copies
+    // two each -- with a warp per row (18 active lanes, one copy each) staging issued as many instructions as the
+    // multiply (ncu: FFMA 41 % of the mix).  Lanes read different rows at the same column; the 32-byte sectors they
+    // touch are reused by the next seven columns out of L1.
     const int rows_total = nc * RT;
-    for (int R = tid >> 5; R < rows_total; R += nthr >> 5) {
+    for (int R = tid; R < rows_total; R += nthr) {
         const int r = R % RT, ci = R / RT;
         const int gy = y0 + r + yofs;
         const bool ok = (unsigned)gy < (unsigned)S;
         const float* sp = src + (long)f * src_bs + ((long)ci * S + (ok ? gy : 0)) * S;
         const unsigned d0 = (unsigned)__cvta_generic_to_shared(sDst + ci * plane + r * PITCH + col0);
         const unsigned nbytes = ok ? 4u : 0u;
-        for (int col = lane; col < S; col += 32)
+#pragma unroll 9
+        for (int col = 0; col < S; ++col)
             asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d0 + 4u * col), "l"(sp + col), "r"(nbytes)
                          : "memory");
     }
@@ -454,8 +458,9 @@ int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kWgTH = 8;                  // rows per staged strip (default; small images are staged whole, WgradArgs::TH)
 
-template <int LOG_QX>
-__global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a) {
+// COB: output channels per owner thread (4; 8 for the cp.async path, halving the input-pixel loads per FMA)
+template <int LOG_QX, int COB>
+__global__ void __launch_bounds__(kConvThreads, COB == 8 ? 2 : 1) conv3x3_wgrad_kernel(WgradArgs a) {
     PAIG_DYN_SMEM(float, smem);
     const int S = a.S, QX = (S + 3) / 4;
     const int PITCH = 4 * QX + 4;
@@ -465,7 +470,8 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
     float* sG = smem + (size_t)a.Cin * in_plane;                      // [Cout][TH][PITCH-4 .. ] pitch 4*QX
     const int GP = 4 * QX;
     const int tid = threadIdx.x;
-    const int cob_n = (a.Cout + 3) / 4;
+    const int cob_n = (a.Cout + COB - 1) / COB;
+    constexpr int kRed = COB * 10;                                    // floats a thread leaves for the final fold
     const int G = cob_n * a.Cin;                                      // owner groups
     const int gsets = gridDim.y;
     const int G_per = (G + gsets - 1) / gsets;                        // groups handled by this CTA (<= 256)
@@ -475,10 +481,10 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
     const bool owner = part < P && grp < G;
     const int ci = owner ? grp % a.Cin : 0, cob = owner ? grp / a.Cin : 0;
 
-    float acc[4][9];
-    float bacc[4];
+    float acc[COB][9];
+    float bacc[COB];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < COB; ++c) {
         bacc[c] = 0.f;
 #pragma unroll
         for (int t = 0; t < 9; ++t) acc[c][t] = 0.f;
@@ -540,9 +546,9 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
                     v[k][0] = p4.x; v[k][1] = p4.y; v[k][2] = p4.z; v[k][3] = p4.w; v[k][4] = p2.x; v[k][5] = p2.y;
                 }
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const int co = cob * 4 + c;
-                    if (co < a.Cout) {
+                for (int c = 0; c < COB; ++c) {
+                    const int co = cob * COB + c;
+                    if (COB == 8 || co < a.Cout) {             // (COB == 8 is only launched when it divides Cout)
                         const float4 g4 = *reinterpret_cast<const float4*>(sG + co * g_plane + r * GP + x0);
                         const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
                         bacc[c] += (gv[0] + gv[1]) + (gv[2] + gv[3]);
@@ -561,31 +567,31 @@ __global__ void __launch_bounds__(kConvThreads) conv3x3_wgrad_kernel(WgradArgs a
         __syncthreads();
     }
     // ---- fold pixel partitions (fixed order) and write this CTA's partial ----
-    float* sRed = smem;                                       // [P][G_per][40]  (reuses the tile area)
+    float* sRed = smem;                                       // [P][G_per][kRed]  (reuses the tile area)
     if (owner) {
-        float* dst = sRed + ((size_t)part * G_per + grp_local) * 40;
+        float* dst = sRed + ((size_t)part * G_per + grp_local) * kRed;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < COB; ++c) {
 #pragma unroll
             for (int t = 0; t < 9; ++t) dst[c * 9 + t] = acc[c][t];
-            dst[36 + c] = bacc[c];
+            dst[COB * 9 + c] = bacc[c];
         }
     }
     __syncthreads();
     const int nW = a.Cout * a.Cin * 9;
     float* out = a.partials + (size_t)blockIdx.x * (nW + a.Cout);
-    for (int e = tid; e < G_per * 40; e += kConvThreads) {
-        const int k = e % 40, gl = e / 40;
+    for (int e = tid; e < G_per * kRed; e += kConvThreads) {
+        const int k = e % kRed, gl = e / kRed;
         const int gg = blockIdx.y * G_per + gl;
         if (gg >= G) continue;
         float s = 0.f;
-        for (int p = 0; p < P; ++p) s += sRed[((size_t)p * G_per + gl) * 40 + k];
+        for (int p = 0; p < P; ++p) s += sRed[((size_t)p * G_per + gl) * kRed + k];
         const int gci = gg % a.Cin, gcob = gg / a.Cin;
-        if (k < 36) {
-            const int co = gcob * 4 + k / 9;
+        if (k < COB * 9) {
+            const int co = gcob * COB + k / 9;
             if (co < a.Cout) out[((size_t)co * a.Cin + gci) * 9 + (k % 9)] = s;
         } else if (gci == 0) {
-            const int co = gcob * 4 + (k - 36);
+            const int co = gcob * COB + (k - COB * 9);
             if (co < a.Cout) out[nW + co] = s;
         }
     }
@@ -689,22 +695,27 @@ int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t s
     if (a.S <= 20) a.TH = a.S <= 10 ? a.S : (a.S + 1) / 2;        // 18 px: two strips of 9, not 8 + 8 + 2
     a.in_plane = pad_plane((a.TH + 2) * PITCH);
     a.g_plane = pad_plane(a.TH * 4 * QX);
-    const int G = ((a.Cout + 3) / 4) * a.Cin;
+    // eight output channels per thread on the cp.async path (decided below; needs Cout % 8 == 0)
+    static const bool async_off = getenv("PAIG_WGRAD_SYNC") != nullptr;
+#ifdef PAIG_EMU
+    const bool want_async = false;
+#else
+    const bool want_async = !async_off && a.S != 4 * QX && !a.in_mask && !a.act;
+#endif
+    const int COB = want_async && a.Cout % 8 == 0 ? 8 : 4;
+    const int G = ((a.Cout + COB - 1) / COB) * a.Cin;
     const int gsets = cdiv(G, kConvThreads);
     const int G_per = cdiv(G, gsets);
     const int P = kConvThreads / G_per > 0 ? kConvThreads / G_per : 1;
     size_t tile = (size_t)a.Cin * a.in_plane + (size_t)a.Cout * a.g_plane;
     // rows the TMA unit cannot address (pitch not a multiple of 16 B): double-buffered cp.async staging when the tile
     // fits twice next to a second CTA and no ReLU mask has to be applied on the way in
-    static const bool async_off = getenv("PAIG_WGRAD_SYNC") != nullptr;
     a.async2 = 0;
-#ifndef PAIG_EMU
-    if (!async_off && a.S != 4 * QX && !a.in_mask && !a.act && 2 * tile * sizeof(float) <= 110 * 1024) {
+    if (want_async && 2 * tile * sizeof(float) <= 110 * 1024) {
         a.async2 = 1;
         tile *= 2;
     }
-#endif
-    const size_t red = (size_t)P * G_per * 40;
+    const size_t red = (size_t)P * G_per * COB * 10;
     const size_t smem = (tile > red ? tile : red) * sizeof(float);
     if (smem > 220 * 1024) {
         set_error("conv3x3_wgrad: %d->%d channels at %d px needs %zu B of shared memory", a.Cin, a.Cout, a.S, smem);
@@ -722,11 +733,13 @@ int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t s
             if (QX == (1 << k)) lq = k;
     const dim3 wg_grid(ctas, gsets), wg_blk(kConvThreads);
     switch (lq) {
-        case 1: launch(conv3x3_wgrad_kernel<1>, wg_grid, wg_blk, smem, st, a); break;
-        case 2: launch(conv3x3_wgrad_kernel<2>, wg_grid, wg_blk, smem, st, a); break;
-        case 3: launch(conv3x3_wgrad_kernel<3>, wg_grid, wg_blk, smem, st, a); break;
-        case 4: launch(conv3x3_wgrad_kernel<4>, wg_grid, wg_blk, smem, st, a); break;
-        default: launch(conv3x3_wgrad_kernel<-1>, wg_grid, wg_blk, smem, st, a);
+        case 1: launch(conv3x3_wgrad_kernel<1, 4>, wg_grid, wg_blk, smem, st, a); break;
+        case 2: launch(conv3x3_wgrad_kernel<2, 4>, wg_grid, wg_blk, smem, st, a); break;
+        case 3: launch(conv3x3_wgrad_kernel<3, 4>, wg_grid, wg_blk, smem, st, a); break;
+        case 4: launch(conv3x3_wgrad_kernel<4, 4>, wg_grid, wg_blk, smem, st, a); break;
+        default:
+            if (COB == 8) launch(conv3x3_wgrad_kernel<-1, 8>, wg_grid, wg_blk, smem, st, a);
+            else launch(conv3x3_wgrad_kernel<-1, 4>, wg_grid, wg_blk, smem, st, a);
     }
     int rc = check_launch(layer_name("conv3x3_wgrad", a.Cin, a.Cout, a.S));
     if (rc) return rc;
