@@ -49,6 +49,7 @@ def test_whole_step_vs_oracle(be, task, B, kw):
 @pytest.mark.parametrize("N,Cin,Cout,S,relu", [
     (3, 3, 8, 32, True), (2, 24, 8, 32, True), (5, 16, 16, 16, False), (19, 32, 32, 8, True),
     (2, 8, 8, 36, True), (3, 16, 16, 18, True), (11, 32, 32, 9, True), (1, 48, 16, 64, True), (2, 128, 32, 8, False),
+    (2, 64, 32, 32, True), (2, 128, 128, 8, False),      # channel blocks of the TMA weight-gradient kernel
 ])
 def test_conv3x3_primitive(be, N, Cin, Cout, S, relu):
     sc.check_conv3x3(be, N, Cin, Cout, S, relu)

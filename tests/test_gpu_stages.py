@@ -37,6 +37,9 @@ def test_decode(be, task, mode):
 @pytest.mark.parametrize("N,Cin,Cout,S,relu", [
     (300, 3, 8, 32, True), (300, 24, 8, 32, True), (257, 16, 16, 16, False), (999, 32, 32, 8, True),
     (64, 8, 8, 36, True), (65, 16, 16, 18, True), (130, 32, 32, 9, True), (20, 48, 16, 64, True), (40, 128, 128, 8, False),
+    # wide layers: channel blocks of the TMA weight-gradient kernel (input x output channel ranges over grid.y), the
+    # cp.async conv3x3; 18-px rows: the cp.async weight-gradient path with 8 channels per thread
+    (37, 64, 32, 32, True), (21, 96, 64, 16, False), (11, 32, 32, 64, True), (150, 32, 16, 18, True), (70, 8, 16, 18, False),
 ])
 def test_conv3x3_primitive(be, N, Cin, Cout, S, relu):
     sc.check_conv3x3(be, N, Cin, Cout, S, relu)
