@@ -992,49 +992,54 @@ int conv1x1_backward(const float* in, long in_bs, int Cin, const float* w, const
 // 2x2 max-pool (blocks.py:281,284) and its adjoint (first maximum in row-major window order wins, as ATen).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) maxpool2_kernel(const float* __restrict__ in, long in_bs, float* __restrict__ out,
-                                                       long out_bs, int C, int So, long total) {
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int x = (int)(idx % So), y = (int)((idx / So) % So), c = (int)((idx / ((long)So * So)) % C);
-    const long f = idx / ((long)So * So * C);
+                                                       long out_bs, int C, int So, int N) {
+    // the frame rides on grid.y: the element index inside a frame is 32-bit (64-bit div/mod per element made these
+    // elementwise kernels compute-bound)
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * So * So) return;
+    const int x = idx % So, y = (idx / So) % So, c = idx / (So * So);
     const int Si = 2 * So;
-    const float* p = in + f * in_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
-    const float m = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[Si], p[Si + 1]));
-    out[f * out_bs + ((long)c * So + y) * So + x] = m;
+    for (long f = blockIdx.y; f < N; f += gridDim.y) {
+        const float* p = in + f * in_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
+        const float m = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[Si], p[Si + 1]));
+        out[f * out_bs + ((long)c * So + y) * So + x] = m;
+    }
 }
 
 // din[window argmax] += dout   (din is the gradient of the pooled tensor's source; other entries untouched)
 __global__ void __launch_bounds__(256) maxpool2_bwd_kernel(const float* __restrict__ in, long in_bs,
                                                            const float* __restrict__ dout, long dout_bs,
                                                            float* __restrict__ din, long din_bs, int C, int So,
-                                                           long total) {
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int x = (int)(idx % So), y = (int)((idx / So) % So), c = (int)((idx / ((long)So * So)) % C);
-    const long f = idx / ((long)So * So * C);
+                                                           int N) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * So * So) return;
+    const int x = idx % So, y = (idx / So) % So, c = idx / (So * So);
     const int Si = 2 * So;
     const long o = ((long)c * Si + 2 * y) * Si + 2 * x;
-    const float* p = in + f * in_bs + o;
-    int best = 0;
-    float m = p[0];
-    if (p[1] > m) { m = p[1]; best = 1; }
-    if (p[Si] > m) { m = p[Si]; best = Si; }
-    if (p[Si + 1] > m) { m = p[Si + 1]; best = Si + 1; }
-    din[f * din_bs + o + best] += dout[f * dout_bs + ((long)c * So + y) * So + x];
+    for (long f = blockIdx.y; f < N; f += gridDim.y) {
+        const float* p = in + f * in_bs + o;
+        int best = 0;
+        float m = p[0];
+        if (p[1] > m) { m = p[1]; best = 1; }
+        if (p[Si] > m) { m = p[Si]; best = Si; }
+        if (p[Si + 1] > m) { m = p[Si + 1]; best = Si + 1; }
+        din[f * din_bs + o + best] += dout[f * dout_bs + ((long)c * So + y) * So + x];
+    }
 }
 
 int maxpool2(const float* in, long in_bs, float* out, long out_bs, int C, int So, int N, cudaStream_t st) {
     const long total = (long)N * C * So * So;
     if (total <= 0) return 0;
-    launch(maxpool2_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, in, in_bs, out, out_bs, C, So, total);
+    launch(maxpool2_kernel, dim3(cdiv((long)C * So * So, 256), N < 32768 ? N : 32768), dim3(256), 0, st, in, in_bs, out, out_bs,
+           C, So, N);
     return check_launch("maxpool2");
 }
 int maxpool2_backward(const float* in, long in_bs, const float* dout, long dout_bs, float* din, long din_bs, int C,
                       int So, int N, cudaStream_t st) {
     const long total = (long)N * C * So * So;
     if (total <= 0) return 0;
-    launch(maxpool2_bwd_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, in, in_bs, dout, dout_bs, din, din_bs, C, So,
-           total);
+    launch(maxpool2_bwd_kernel, dim3(cdiv((long)C * So * So, 256), N < 32768 ? N : 32768), dim3(256), 0, st, in, in_bs, dout,
+           dout_bs, din, din_bs, C, So, N);
     return check_launch("maxpool2_bwd");
 }
 
@@ -1114,30 +1119,31 @@ __device__ __forceinline__ void up_adj(int i, int Si, int& o0, float (&w)[4]) {
 
 __global__ void __launch_bounds__(256) upsample2_bwd_kernel(const float* __restrict__ dout, long dout_bs,
                                                             float* __restrict__ din, long din_bs, int C, int Si,
-                                                            long total) {
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
+                                                            int N) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= C * Si * Si) return;
     const int So = 2 * Si;
-    const int j = (int)(idx % Si), i = (int)((idx / Si) % Si), c = (int)((idx / ((long)Si * Si)) % C);
-    const long f = idx / ((long)Si * Si * C);
-    const float* g = dout + f * dout_bs + (long)c * So * So;
+    const int j = idx % Si, i = (idx / Si) % Si, c = idx / (Si * Si);
     int oy0, ox0;
     float wy[4], wx[4];
     up_adj(i, Si, oy0, wy);
     up_adj(j, Si, ox0, wx);
-    float s = 0.f;
+    for (long f = blockIdx.y; f < N; f += gridDim.y) {
+        const float* g = dout + f * dout_bs + (long)c * So * So;
+        float s = 0.f;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int oy = oy0 + a;
-        if (wy[a] == 0.f) continue;
-        const float* row = g + oy * So + ox0;
-        float r = 0.f;
+        for (int a = 0; a < 4; ++a) {
+            const int oy = oy0 + a;
+            if (wy[a] == 0.f) continue;
+            const float* row = g + oy * So + ox0;
+            float r = 0.f;
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-            if (wx[b] != 0.f) r += wx[b] * row[b];
-        s += wy[a] * r;
+            for (int b = 0; b < 4; ++b)
+                if (wx[b] != 0.f) r += wx[b] * row[b];
+            s += wy[a] * r;
+        }
+        din[f * din_bs + ((long)c * Si + i) * Si + j] = s;
     }
-    din[f * din_bs + ((long)c * Si + i) * Si + j] = s;
 }
 
 int upsample2(const float* in, long in_bs, float* out, long out_bs, int C, int Si, int N, cudaStream_t st) {
@@ -1154,7 +1160,8 @@ int upsample2(const float* in, long in_bs, float* out, long out_bs, int C, int S
 int upsample2_backward(const float* dout, long dout_bs, float* din, long din_bs, int C, int Si, int N, cudaStream_t st) {
     const long total = (long)N * C * Si * Si;
     if (total <= 0) return 0;
-    launch(upsample2_bwd_kernel, dim3(cdiv(total, 256)), dim3(256), 0, st, dout, dout_bs, din, din_bs, C, Si, total);
+    launch(upsample2_bwd_kernel, dim3(cdiv((long)C * Si * Si, 256), N < 32768 ? N : 32768), dim3(256), 0, st, dout, dout_bs,
+           din, din_bs, C, Si, N);
     return check_launch("upsample2_bwd");
 }
 
