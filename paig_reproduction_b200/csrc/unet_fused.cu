@@ -144,7 +144,7 @@ __device__ __forceinline__ void conv_accumulate(float (&acc)[PY][CO][4], const f
                                                 const Geo g, const float* __restrict__ w, int y, int qx) {
     const float* r0 = planes + y * g.P + 4 * qx;
     const int plane = g.plane, P = g.P;
-#pragma unroll 2
+#pragma unroll 1
     for (int ci = 0; ci < nci; ++ci) {
         float v[PY + 2][6];
 #pragma unroll
@@ -335,9 +335,15 @@ __device__ __forceinline__ void run_conv(const FusedOp& op, float* sm, int f, in
                                                                        ((long)(cg * CO + c) * op.S + y + r) * op.S + 4 * qx));
             }
 #endif
-            conv_accumulate<CO, COUT, PY>(acc, sm + op.in0, op.Cin0, g, w + cg * CO, y, qx);
-            if (op.Cin1)
-                conv_accumulate<CO, COUT, PY>(acc, sm + op.in1, op.Cin1, g, w + op.Cin0 * 9 * COUT + cg * CO, y, qx);
+            // the two input segments of a concat share one copy of the accumulate loop (code size: the kernel's
+            // instruction footprint per frame is what the instruction cache has to hold)
+#pragma unroll 1
+            for (int seg = 0; seg < 2; ++seg) {
+                const int nci = seg ? op.Cin1 : op.Cin0;
+                if (nci)
+                    conv_accumulate<CO, COUT, PY>(acc, sm + (seg ? op.in1 : op.in0), nci, g,
+                                                  w + (seg ? op.Cin0 * 9 * COUT : 0) + cg * CO, y, qx);
+            }
             PAIG_STAMP(tm, 2);
             conv_epilogue<CO, PY>(acc, op, g, sm, bias, cg, y, qx, f);
         }
