@@ -391,6 +391,24 @@ int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
     if (a.N <= 0) return 0;
     int strips;
     conv_geometry(a.S, a.N, &a.QX, &a.TH, &a.FPB, &strips);
+    // the frame groups ride on grid.z (<= 65535): very large batches (the 8192-sequence evaluation sweep is 81 920
+    // frames) go out as several launches over consecutive frame ranges
+    {
+        const long max_frames = 65535L * a.FPB;
+        if (a.N > max_frames) {
+            for (long f0 = 0; f0 < in_args.N; f0 += max_frames) {
+                ConvArgs part = in_args;
+                part.N = (int)(in_args.N - f0 < max_frames ? in_args.N - f0 : max_frames);
+                part.in = in_args.in + f0 * in_args.in_bs;
+                part.out = in_args.out + f0 * in_args.out_bs;
+                if (in_args.mask) part.mask = in_args.mask + f0 * in_args.mask_bs;
+                // (conv_geometry may pick a different FPB for the tail; every range is a self-contained launch)
+                const int rc = conv3x3(part, st);
+                if (rc) return rc;
+            }
+            return 0;
+        }
+    }
     const int PITCH = 4 * a.QX + 4;
     const int threads = ((a.FPB * a.TH * a.QX + 31) / 32) * 32;
     const bool wide = (a.Cout % 16) == 0;

@@ -87,3 +87,31 @@ def _dump_report(name, report):
         json.dump(data, open(path, "w"), indent=1)
     except OSError:
         pass
+
+
+def test_conv3x3_forward_beyond_65535_frame_groups():
+    """Size property at the evaluation sweep's scale (8192 sequences x 10 frames = 81 920 frames through the per-layer
+    path of the 64-px task): frame groups ride on grid.z, so conv3x3 splits such batches over several launches; the
+    first, the last and the frames around the split must equal a plain fp32 convolution of the same frames."""
+    import torch
+    import torch.nn.functional as F
+    from paig_reproduction_b200 import _lib
+    lib = _lib.load()
+    N, Cin, Cout, S = 65535 + 91, 8, 8, 32                      # FPB = 1 at 32 px: 65 626 frame groups
+    g = torch.Generator(device="cuda:0").manual_seed(3)
+    x = torch.rand(N, Cin, S, S, device="cuda:0", generator=g)
+    w = (torch.rand(Cout, Cin, 3, 3, device="cuda:0", generator=g) - 0.5) / 6.0
+    b = torch.rand(Cout, device="cuda:0", generator=g) - 0.5
+    y = torch.full((N, Cout, S, S), 7.0, device="cuda:0")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.paig_conv3x3_forward(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), N, Cin, Cout, S, 1, st))
+    torch.cuda.synchronize()
+    prev = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        for lo, hi in ((0, 64), (65535 - 32, 65535 + 32), (N - 64, N)):
+            ref = F.relu(F.conv2d(x[lo:hi].double(), w.double(), b.double(), padding=1)).float()
+            err = (y[lo:hi] - ref).abs().max().item()
+            assert err <= 2e-5 * max(ref.abs().max().item(), 1.0), (lo, hi, err)
+    finally:
+        torch.backends.cudnn.allow_tf32 = prev
