@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PAIG_ABI_VERSION 1
+#define PAIG_ABI_VERSION 2
 
 enum { PAIG_CELL_SPRING = 0, PAIG_CELL_BOUNCING = 1, PAIG_CELL_GRAVITY = 2 };
 
@@ -42,7 +42,14 @@ typedef struct paig_task {
     int32_t deep_unet;    /* 0: ShallowUNet (H<40), 1: UNet (blocks.py:79-82) */
     float alpha;          /* --autoencoder_loss weight, physics_models.py:137-139 */
     int32_t batch_global; /* B of the whole job: loss normalisers use it (data-parallel shards pass the same value) */
+    float gravity_A;      /* 0: the gravity cell evaluates A = exp(g) exp(2m) at every forward (default; dL/dg flows).
+                           * > 0: use this value instead -- the reference computes A ONCE in the cell's constructor
+                           * (cells.py:92-94), so a checkpoint with g != 0 still rolls out with the
+                           * constructor-time A there; pass that A here to reproduce it. */
+    int32_t flags;        /* PAIG_FLAG_* */
 } paig_task;
+
+enum { PAIG_FLAG_INFERENCE = 1 /* forward only: keep nothing for backward (eval_performance, base.py:174-218) */ };
 
 /* weight/bias pair of one Linear or Conv2d; NULL where the layer is absent or (in a gradient table) dead. */
 typedef struct paig_wb {
@@ -127,7 +134,8 @@ int paig_rollout_forward(int cell, int n_objs, int B, int steps, const float* dt
                          const double* phys1, float* pos_vel_seq, void* stream);
 
 /* Reverse sweep.  d_seq: [B, steps+1, 4n] upstream gradient of every row of pos_vel_seq (pos and vel parts).
- * d_state0: [B, 4n] receives dL/d(initial pos||vel).  d_phys: [2] fp64, WRITTEN (dk, dequil | dg, 0). */
+ * d_state0: [B, 4n] receives dL/d(initial pos||vel).  d_phys: [2] fp64, WRITTEN (dk, dequil | dg, 0 | 0, 0).
+ * The sum over sequences runs in a fixed order for any B (run-to-run bit-identical). */
 int paig_rollout_backward(int cell, int n_objs, int B, int steps, const float* dt, const double* phys0,
                           const double* phys1, const float* pos_vel_seq, const float* d_seq, float* d_state0,
                           double* d_phys, void* stream);
@@ -145,6 +153,13 @@ int paig_templates_backward(const paig_task* t, const paig_params* p, const paig
  * target frame f lives at target + (f / frames_per_seq) * target_seq_stride + (f % frames_per_seq) * 3*H*H. */
 int paig_decode_forward(const paig_task* t, const float* consts, const float* loc, int F, float* frames,
                         const float* target, long target_seq_stride, int frames_per_seq, float* sse, void* stream);
+
+/* The decoder's per-layer intermediates the reference caches as self.transf_contents / self.transf_masks
+ * (physics_models.py:190,196) for F frames: transf_contents, transf_masks: [n+1][F][3][H][H] -- layer o < n is
+ * object o's bilinear-sampled sigmoid(content) / its softmax weight (repeated over the 3 channels, as the
+ * reference's tiled template makes it), layer n the background. */
+int paig_decode_layers(const paig_task* t, const float* consts, const float* loc, int F, float* transf_contents,
+                       float* transf_masks, void* stream);
 
 /* Decoder backward.  Either d_frames [F,3,H,H] is given, or (d_frames == NULL) the gradient is formed
  * in-kernel as 2*scale[f % frames_per_seq]*(frame - target) (scale: device [frames_per_seq]).  d_loc [F,2n] is

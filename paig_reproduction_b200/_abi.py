@@ -3,14 +3,18 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 CELL_IDS = {"spring": 0, "bouncing": 1, "gravity": 2}
 
 
 class Task(C.Structure):
     _fields_ = [("cell", C.c_int32), ("n_objs", C.c_int32), ("H", C.c_int32), ("seq_len", C.c_int32),
                 ("input_steps", C.c_int32), ("pred_steps", C.c_int32), ("alt_vel", C.c_int32),
-                ("deep_unet", C.c_int32), ("alpha", C.c_float), ("batch_global", C.c_int32)]
+                ("deep_unet", C.c_int32), ("alpha", C.c_float), ("batch_global", C.c_int32),
+                ("gravity_A", C.c_float), ("flags", C.c_int32)]
+
+
+FLAG_INFERENCE = 1
 
 
 class WB(C.Structure):
@@ -87,6 +91,7 @@ def declare(lib):
         "paig_templates_backward": (i, [PT, PP, PP, vp, vp, vp, vp, vp]),
         "paig_decode_forward": (i, [PT, vp, vp, i, vp, vp, l, i, vp, vp]),
         "paig_decode_backward": (i, [PT, vp, vp, i, vp, vp, l, i, vp, vp, vp, vp, vp, vp]),
+        "paig_decode_layers": (i, [PT, vp, vp, i, vp, vp, vp]),
         "paig_encoder_forward": (i, [PT, PP, vp, l, i, i, vp, vp, vp, vp, vp]),
         "paig_encoder_backward": (i, [PT, PP, PP, vp, l, i, i, vp, vp, vp]),
         "paig_velocity_forward": (i, [PT, PP, vp, i, vp, vp, vp]),
@@ -121,7 +126,7 @@ def declare(lib):
 
 EXPORTS = ["paig_abi_version", "paig_last_error", "paig_workspace_bytes", "paig_step_forward", "paig_step_backward",
            "paig_step_fused", "paig_step_fused_host", "paig_rollout_forward", "paig_rollout_backward",
-           "paig_templates_forward", "paig_templates_backward", "paig_decode_forward", "paig_decode_backward",
+           "paig_templates_forward", "paig_templates_backward", "paig_decode_forward", "paig_decode_backward", "paig_decode_layers",
            "paig_encoder_forward", "paig_encoder_backward", "paig_velocity_forward", "paig_velocity_backward",
            "paig_conv3x3_forward", "paig_conv3x3_backward", "paig_debug_workspace_offset", "paig_debug_unet_conv_view",
            "paig_frame_sse_forward", "paig_frame_sse_backward", "paig_launch_count", "paig_profile_begin",

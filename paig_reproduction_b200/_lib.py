@@ -33,6 +33,9 @@ def load():
         raise PaigError("libpaig_b200.so lacks symbols declared in include/paig_b200.h: %s" % ", ".join(missing))
     if lib.paig_abi_version() != _abi.ABI_VERSION:
         raise PaigError("libpaig_b200.so ABI %d != expected %d" % (lib.paig_abi_version(), _abi.ABI_VERSION))
+    if os.environ.get("PAIG_TRACE_LIB"):
+        import sys
+        sys.stderr.write("paig: loaded %s (ABI %d)\n" % (LIB_PATH, lib.paig_abi_version()))
     _lib = lib
     return lib
 

@@ -149,15 +149,17 @@ int paig_profile_end(char* buf, size_t cap) {
 
 int paig_rollout_forward(int cell, int n_objs, int B, int steps, const float* dt, const double* phys0,
                          const double* phys1, float* pos_vel_seq, void* stream) {
-    return rollout_forward(cell, n_objs, B, steps, dt, phys0, phys1, pos_vel_seq, (cudaStream_t)stream);
+    return rollout_forward(cell, n_objs, B, steps, dt, phys0, phys1, 0.f, pos_vel_seq, (cudaStream_t)stream);
 }
 
 int paig_rollout_backward(int cell, int n_objs, int B, int steps, const float* dt, const double* phys0,
                           const double* phys1, const float* pos_vel_seq, const float* d_seq, float* d_state0,
                           double* d_phys, void* stream) {
     const long rs = 4L * n_objs;
-    return rollout_backward(cell, n_objs, B, steps, dt, phys0, phys1, pos_vel_seq, d_seq, d_seq + 2 * n_objs,
-                            (steps + 1) * rs, rs, 1, d_state0, d_phys, (cudaStream_t)stream);
+    if (cell == PAIG_CELL_BOUNCING && d_phys) cudaMemsetAsync(d_phys, 0, 2 * sizeof(double), (cudaStream_t)stream);
+    return rollout_backward(cell, n_objs, B, steps, dt, phys0, phys1, 0.f, pos_vel_seq, d_seq, d_seq + 2 * n_objs,
+                            (steps + 1) * rs, rs, 1, d_state0, d_phys, d_phys ? d_phys + 1 : nullptr, nullptr,
+                            (cudaStream_t)stream);   // no scratch: one block walks all sequences (fixed order)
 }
 
 int paig_templates_forward(const paig_task* t, const paig_params* p, float* raw, float* consts, float* hidden,
@@ -191,6 +193,17 @@ int paig_decode_forward(const paig_task* t, const float* consts, const float* lo
     DecSeg a = flat_segment(t, loc, F, target, target_seq_stride, frames_per_seq), b;
     a.frames = frames;
     a.sse = target ? sse : nullptr;
+    return decode_run(t, consts, a, b, false, nullptr, nullptr, 0, (cudaStream_t)stream);
+}
+
+int paig_decode_layers(const paig_task* t, const float* consts, const float* loc, int F, float* transf_contents,
+                       float* transf_masks, void* stream) {
+    if (!valid_task(t)) return 1;
+    if (!transf_contents || !transf_masks) { set_error("decode_layers: both outputs are required"); return 1; }
+    DecSeg a = flat_segment(t, loc, F, nullptr, 0, 1), b;
+    a.layer_c = transf_contents;
+    a.layer_m = transf_masks;
+    a.layer_stride = (long)F * 3 * t->H * t->H;
     return decode_run(t, consts, a, b, false, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 

@@ -55,7 +55,8 @@ __device__ __forceinline__ Tap make_tap(int j, float l, int H, int t) {
 // NOBJ*4*(H*H + H*H/2) extra floats; larger frames (64 px) keep the atomic path.
 template <int NOBJ, bool BWD, bool GATHER>
 __global__ void __launch_bounds__(kDecThreads)
-decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB, float* __restrict__ partials) {
+decode_kernel(int H, int band_rows, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
+              float* __restrict__ partials) {
     const int t = H / 2, tt = t * t, HW = H * H;
     const int CN = NOBJ * tt * 4 + 3 * HW;           // floats in the constants block
     const int tid = threadIdx.x;
@@ -72,9 +73,13 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
     float* sYw1 = reinterpret_cast<float*>(sY0) + NOBJ * H;
     float* sYw0 = sYw1 + NOBJ * H;
     float* sRed = sYw0 + NOBJ * H;                    // [8 warps][2*NOBJ+1]
-    float* sD = sRed + 8 * (2 * NOBJ + 1);            // GATHER: [NOBJ*4][H][H] per-pixel dL | dC0..2
-    float* sE = sD + (GATHER ? NOBJ * 4 * HW : 0);    // GATHER: [NOBJ*4][H][t] after the x pass
-    float* sInv = sE + (GATHER ? NOBJ * 4 * H * t : 0);   // GATHER: [2 axes][NOBJ][t][8]: first contributor, 6 weights
+    // GATHER works on bands of `band_rows` image rows (the whole frame at 32 / 36 px, 16 rows at 64 px where a full
+    // frame of per-pixel upstream values does not fit next to the constants): bands are walked in order, so the
+    // texel sums keep one fixed order
+    const int BH = band_rows * H;
+    float* sD = sRed + 8 * (2 * NOBJ + 1);            // GATHER: [NOBJ*4][band][H] per-pixel dL | dC0..2
+    float* sE = sD + (GATHER ? NOBJ * 4 * BH : 0);    // GATHER: [NOBJ*4][band][t] after the x pass
+    float* sInv = sE + (GATHER ? NOBJ * 4 * band_rows * t : 0);   // GATHER: [2 axes][NOBJ][t][8]: first contributor, 6 weights
     __shared__ __align__(8) unsigned long long bar;
 
     stage_bulk(smem, consts, (unsigned)(CN * sizeof(float)), &bar, 0);
@@ -84,7 +89,7 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
     __syncthreads();
 
     const int F = segA.nframes + segB.nframes;
-    const int quads_per_row = H / 4, nquads = HW / 4;
+    const int quads_per_row = H / 4;
     for (int f = blockIdx.x; f < F; f += gridDim.x) {
         const bool inA = f < segA.nframes;
         const DecSeg& sg = inA ? segA : segB;
@@ -113,8 +118,35 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
 #pragma unroll
         for (int k = 0; k < 2 * NOBJ + 1; ++k) acc[k] = 0.f;
 
-        for (int qd = tid; qd < nquads; qd += kDecThreads) {
-            const int i = qd / quads_per_row, j0 = (qd % quads_per_row) * 4;
+        if (GATHER && BWD && do_bwd) {
+            // inverse tap tables: texel x of object o hears from columns j with x0(j) == x (weight w0) or x0(j) + 1 == x
+            // (weight w1).  x0 is non-decreasing and grows by one every two columns, so the contributors are <= 6
+            // consecutive columns starting at the first j with x0(j) >= x - 1.
+            for (int e = tid; e < 2 * NOBJ * t; e += kDecThreads) {
+                const int x = e % t, o = (e / t) % NOBJ, axis = e / (t * NOBJ);
+                const int* i0 = (axis ? sY0 : sX0) + o * H;
+                const float* w0 = (axis ? sYw0 : sXw0) + o * H;
+                const float* w1 = (axis ? sYw1 : sXw1) + o * H;
+                int j = 2 * (x - 1 - i0[0]) - 1;                       // analytic guess, then settle on the exact first column
+                j = min(max(j, 0), H - 1);
+                while (j > 0 && i0[j - 1] >= x - 1) --j;
+                while (j < H && i0[j] < x - 1) ++j;
+                float* dst = sInv + (size_t)e * 8;
+                reinterpret_cast<int*>(dst)[0] = j;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    const int jj = j + k;
+                    float w = 0.f;
+                    if (jj < H) w = i0[jj] == x ? w0[jj] : (i0[jj] + 1 == x ? w1[jj] : 0.f);
+                    dst[1 + k] = w;
+                }
+            }
+        }
+
+        for (int band0 = 0; band0 < H; band0 += band_rows) {
+        const int brows = min(band_rows, H - band0);
+        for (int qd = tid; qd < brows * quads_per_row; qd += kDecThreads) {
+            const int i = band0 + qd / quads_per_row, j0 = (qd % quads_per_row) * 4;
             float out[3][4];
             float wgt[4][NOBJ + 1];
             float col[4][NOBJ][3];
@@ -170,6 +202,23 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
                     *reinterpret_cast<float4*>(frame + c * HW + i * H + j0) =
                         make_float4(out[c][0], out[c][1], out[c][2], out[c][3]);
             }
+            if (!BWD && sg.layer_c) {
+                // physics_models.py:190,196: per-layer sampled contents and softmax masks of this decoder call,
+                // [n+1][F][3][H][H] each (object layers, then the background; masks repeated over the 3 channels)
+#pragma unroll
+                for (int o = 0; o <= NOBJ; ++o) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const long at = (long)o * sg.layer_stride + (long)fl * 3 * HW + c * HW + i * H + j0;
+                        float4 cv;
+                        if (o < NOBJ) cv = make_float4(col[0][o < NOBJ ? o : 0][c], col[1][o < NOBJ ? o : 0][c],
+                                                       col[2][o < NOBJ ? o : 0][c], col[3][o < NOBJ ? o : 0][c]);
+                        else cv = *reinterpret_cast<const float4*>(sSB + c * HW + i * H + j0);
+                        *reinterpret_cast<float4*>(sg.layer_c + at) = cv;
+                        *reinterpret_cast<float4*>(sg.layer_m + at) = make_float4(wgt[0][o], wgt[1][o], wgt[2][o], wgt[3][o]);
+                    }
+                }
+            }
             float G[3][4];
             if (tgt) {
 #pragma unroll
@@ -214,9 +263,9 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
                         const float wx1 = sXw1[o * H + j], wx0 = sXw0[o * H + j];
                         const float wy1 = sYw1[o * H + i], wy0 = sYw0[o * H + i];
                         if (GATHER) {
-                            sD[(o * 4 + 0) * HW + i * H + j] = dL;
+                            sD[(o * 4 + 0) * BH + (i - band0) * H + j] = dL;
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) sD[(o * 4 + 1 + c) * HW + i * H + j] = dC[c];
+                            for (int c = 0; c < 3; ++c) sD[(o * 4 + 1 + c) * BH + (i - band0) * H + j] = dC[c];
                         }
                         float gix = 0.f, giy = 0.f;
 #pragma unroll
@@ -249,6 +298,45 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
                 }
             }
         }
+        if (GATHER && BWD && do_bwd) {
+            __syncthreads();                          // this band's sD complete (and sInv, on the first band)
+            // x pass: E[oc][i][x] = sum_k w[k] D[oc][i][jlo + k]; a thread keeps one (oc, x) and walks the band's rows
+            for (int e = tid; e < NOBJ * 4 * t; e += kDecThreads) {
+                const int x = e % t, oc = e / t, o = oc >> 2;
+                const float* inv = sInv + (size_t)(o * t + x) * 8;
+                const int jlo = reinterpret_cast<const int*>(inv)[0];
+                float w[6];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w[k] = inv[1 + k];
+                const int nk = min(6, H - jlo);
+                for (int il = 0; il < brows; ++il) {
+                    const float* row = sD + oc * BH + il * H + jlo;
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        if (k < nk) s += w[k] * row[k];
+                    sE[(oc * band_rows + il) * t + x] = s;
+                }
+            }
+            __syncthreads();
+            // y pass over the rows of this band, accumulated into this CTA's gradient block by the texel's only owner
+            for (int e = tid; e < NOBJ * 4 * tt; e += kDecThreads) {
+                const int x = e % t, y = (e / t) % t, oc = e / tt, o = oc >> 2, ch = oc & 3;
+                const float* inv = sInv + (size_t)((NOBJ + o) * t + y) * 8;
+                const int ilo = reinterpret_cast<const int*>(inv)[0];
+                const int k0 = max(0, band0 - ilo), k1 = min(6, min(H, band0 + brows) - ilo);
+                if (k0 < k1) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        if (k >= k0 && k < k1) s += inv[1 + k] * sE[(oc * band_rows + (ilo + k - band0)) * t + x];
+                    float* dst = ch == 0 ? sG + o * tt : sG + NOBJ * tt + (o * 3 + ch - 1) * tt;
+                    dst[y * t + x] += s;
+                }
+            }
+            if (band0 + band_rows < H) __syncthreads();   // the next band rewrites sD / sE
+        }
+        }   // bands
         // ---- per-frame reductions: d loc (2 per object) and the squared error ----
         constexpr int NR = 2 * NOBJ + 1;
         const int warp = tid >> 5, lane = tid & 31;
@@ -258,63 +346,6 @@ decode_kernel(int H, const float* __restrict__ consts, DecSeg segA, DecSeg segB,
             if (lane == 0) sRed[warp * NR + k] = v;
         }
         __syncthreads();
-        if (GATHER && BWD && do_bwd) {
-            // inverse tap tables: texel x of object o hears from columns j with x0(j) == x (weight w0) or x0(j) + 1 == x
-            // (weight w1).  x0 is non-decreasing and grows by one every two columns, so the contributors are <= 6
-            // consecutive columns starting at the first j with x0(j) >= x - 1.
-            for (int e = tid; e < 2 * NOBJ * t; e += kDecThreads) {
-                const int x = e % t, o = (e / t) % NOBJ, axis = e / (t * NOBJ);
-                const int* i0 = (axis ? sY0 : sX0) + o * H;
-                const float* w0 = (axis ? sYw0 : sXw0) + o * H;
-                const float* w1 = (axis ? sYw1 : sXw1) + o * H;
-                int j = 2 * (x - 1 - i0[0]) - 1;                       // analytic guess, then settle on the exact first column
-                j = min(max(j, 0), H - 1);
-                while (j > 0 && i0[j - 1] >= x - 1) --j;
-                while (j < H && i0[j] < x - 1) ++j;
-                float* dst = sInv + (size_t)e * 8;
-                reinterpret_cast<int*>(dst)[0] = j;
-#pragma unroll
-                for (int k = 0; k < 6; ++k) {
-                    const int jj = j + k;
-                    float w = 0.f;
-                    if (jj < H) w = i0[jj] == x ? w0[jj] : (i0[jj] + 1 == x ? w1[jj] : 0.f);
-                    dst[1 + k] = w;
-                }
-            }
-            __syncthreads();
-            // x pass: E[oc][i][x] = sum_k w[k] D[oc][i][jlo + k]; a thread keeps one (oc, x) and walks the rows
-            for (int e = tid; e < NOBJ * 4 * t; e += kDecThreads) {
-                const int x = e % t, oc = e / t, o = oc >> 2;
-                const float* inv = sInv + (size_t)(o * t + x) * 8;
-                const int jlo = reinterpret_cast<const int*>(inv)[0];
-                float w[6];
-#pragma unroll
-                for (int k = 0; k < 6; ++k) w[k] = inv[1 + k];
-                const int nk = min(6, H - jlo);
-                for (int i = 0; i < H; ++i) {
-                    const float* row = sD + oc * HW + i * H + jlo;
-                    float s = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k)
-                        if (k < nk) s += w[k] * row[k];
-                    sE[(oc * H + i) * t + x] = s;
-                }
-            }
-            __syncthreads();
-            // y pass, accumulated into this CTA's gradient block by the texel's only owner
-            for (int e = tid; e < NOBJ * 4 * tt; e += kDecThreads) {
-                const int x = e % t, y = (e / t) % t, oc = e / tt, o = oc >> 2, ch = oc & 3;
-                const float* inv = sInv + (size_t)((NOBJ + o) * t + y) * 8;
-                const int ilo = reinterpret_cast<const int*>(inv)[0];
-                const int nk = min(6, H - ilo);
-                float s = 0.f;
-#pragma unroll
-                for (int k = 0; k < 6; ++k)
-                    if (k < nk) s += inv[1 + k] * sE[(oc * H + ilo + k) * t + x];
-                float* dst = ch == 0 ? sG + o * tt : sG + NOBJ * tt + (o * 3 + ch - 1) * tt;
-                dst[y * t + x] += s;
-            }
-        }
         if (tid < NR) {
             float s = 0.f;
             for (int w = 0; w < kDecThreads / 32; ++w) s += sRed[w * NR + tid];
@@ -365,15 +396,25 @@ static int run_decode(const Dims& d, const float* consts, const DecSeg& a, const
     const int grid = decode_grid(F);
     const size_t tab = (size_t)6 * NOBJ * d.H + 8 * (2 * NOBJ + 1);
     if (bwd) {
-        const size_t gather_fl = (size_t)NOBJ * 4 * (d.HW + d.H * d.t) + (size_t)2 * NOBJ * d.t * 8;
-        const size_t smem_g = ((size_t)2 * CN + tab + gather_fl) * sizeof(float);
         static const bool atomics = getenv("PAIG_DECODE_ATOMICS") != nullptr;
         // Three objects need > 200 registers per thread: one CTA per SM whatever the shared-memory footprint, so the
-        // gather tables may take the whole SM (3bp, 36 px: 162 KB) and the grid is one CTA per SM.
-        const bool one_cta = NOBJ >= 3;
-        if (!atomics && smem_g <= (size_t)(one_cta ? 220 : 110) * 1024) {
+        // gather tables may take the whole SM (3bp, 36 px: 162 KB) and the grid is one CTA per SM.  At 64 px the
+        // constants and their gradient block alone are 160 KB: one CTA per SM as well, and the gather runs over bands
+        // of rows (the largest band that fits), which keeps the decoder backward deterministic at every frame size.
+        auto smem_for = [&](int band) {
+            const size_t gather_fl = (size_t)NOBJ * 4 * band * (d.H + d.t) + (size_t)2 * NOBJ * d.t * 8;
+            return ((size_t)2 * CN + tab + gather_fl) * sizeof(float);
+        };
+        int band = d.H;
+        bool one_cta = NOBJ >= 3;
+        if (smem_for(band) > (size_t)(one_cta ? 220 : 110) * 1024) {
+            one_cta = true;
+            while (band > 4 && smem_for(band) > (size_t)220 * 1024) band = (band + 1) / 2;
+        }
+        if (!atomics && smem_for(band) <= (size_t)(one_cta ? 220 : 110) * 1024) {
             const int g1 = one_cta && grid > 148 ? 148 : grid;
-            launch(decode_kernel<NOBJ, true, true>, dim3(g1), dim3(kDecThreads), smem_g, st, d.H, consts, a, b, partials);
+            launch(decode_kernel<NOBJ, true, true>, dim3(g1), dim3(kDecThreads), smem_for(band), st, d.H, band, consts, a, b,
+                   partials);
             int rc = check_launch("decode_bwd");
             if (rc) return rc;
             launch(decode_reduce_kernel, dim3(cdiv(CN, 256)), dim3(256), 0, st, (const float*)partials, g1, CN, d_consts,
@@ -381,7 +422,7 @@ static int run_decode(const Dims& d, const float* consts, const DecSeg& a, const
             return check_launch("decode_reduce");
         } else {
             const size_t smem = ((size_t)2 * CN + tab) * sizeof(float);
-            launch(decode_kernel<NOBJ, true, false>, dim3(grid), dim3(kDecThreads), smem, st, d.H, consts, a, b, partials);
+            launch(decode_kernel<NOBJ, true, false>, dim3(grid), dim3(kDecThreads), smem, st, d.H, d.H, consts, a, b, partials);
         }
         int rc = check_launch("decode_bwd");
         if (rc) return rc;
@@ -390,7 +431,7 @@ static int run_decode(const Dims& d, const float* consts, const DecSeg& a, const
         return check_launch("decode_reduce");
     }
     const size_t smem = ((size_t)CN + tab) * sizeof(float);
-    launch(decode_kernel<NOBJ, false, false>, dim3(grid), dim3(kDecThreads), smem, st, d.H, consts, a, b, (float*)nullptr);
+    launch(decode_kernel<NOBJ, false, false>, dim3(grid), dim3(kDecThreads), smem, st, d.H, d.H, consts, a, b, (float*)nullptr);
     return check_launch("decode_fwd");
 }
 

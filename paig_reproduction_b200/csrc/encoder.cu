@@ -169,7 +169,7 @@ Layout make_layout(const paig_task* t, int B) {
     L.sse = take((size_t)B * (d.e + d.steps));
     L.scales = take(d.e + d.steps);
     L.losses = take(8);
-    L.dphys = take(8);
+    L.dphys = take(2 * rollout_scratch_doubles(B));   // arrival counter + per-block fp64 partials of the rollout backward
     {   // room for the split-K partials of encoder.l1 forward ([splits][nN][200]) and weight gradient ([splits][200][K])
         const size_t fwd = (size_t)cdiv(L.K, 256) * nN * kHidden, wg = 4 * (size_t)kHidden * L.K;
         const size_t sk = fwd > wg ? fwd : wg;

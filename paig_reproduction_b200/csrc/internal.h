@@ -7,11 +7,13 @@ namespace paig {
 bool valid_task(const paig_task* t);
 
 // rollout.cu
-int rollout_forward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1, float* seq,
-                    cudaStream_t st);
+// a_frozen: 0, or the gravity cell's constructor-time A (paig_task.gravity_A)
+int rollout_forward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1,
+                    float a_frozen, float* seq, cudaStream_t st);
 int rollout_backward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1,
-                     const float* seq, const float* dpos, const float* dvel, long batch_stride, long row_stride,
-                     int with_row0, float* d_state0, double* d_phys, cudaStream_t st);
+                     float a_frozen, const float* seq, const float* dpos, const float* dvel, long batch_stride, long row_stride,
+                     int with_row0, float* d_state0, double* d_phys0, double* d_phys1, double* scratch, cudaStream_t st);
+inline size_t rollout_scratch_doubles(int B) { return 2 + 2 * (size_t)((B + 127) / 128); }
 
 // decoder.cu -- a run of frames sharing one indexing rule (recons frames of all sequences, or rollout frames)
 struct DecSeg {
@@ -27,6 +29,9 @@ struct DecSeg {
     float* sse = nullptr;            // [nframes] sum of squared error vs target (nullable)
     float* dloc = nullptr;           // gradient wrt loc, indexed like loc with its own strides (nullable)
     long dloc_seq_stride = 0, dloc_row_stride = 0;
+    float* layer_c = nullptr;        // forward only, nullable: [n+1][nframes][3][H][H] per-layer contents (transf_contents)
+    float* layer_m = nullptr;        //   and softmax masks (transf_masks); layer_stride = nframes*3*H*H
+    long layer_stride = 0;
 };
 int decode_run(const paig_task* t, const float* consts, const DecSeg& a, const DecSeg& b, bool bwd, float* partials,
                float* d_consts, int accumulate, cudaStream_t st);

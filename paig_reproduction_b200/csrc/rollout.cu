@@ -22,7 +22,9 @@ struct Phys {
     float b;     // spring: (float)(2*exp(equil))
 };
 
-__device__ __forceinline__ Phys load_phys(int cell, const float* dt, const double* p0, const double* p1) {
+// a_frozen > 0: the gravity cell uses this A instead of exp(g) exp(2m) (the reference evaluates A once, in the cell's
+// constructor, cells.py:92-94 -- SURVEY Q3; paig_task.gravity_A)
+__device__ __forceinline__ Phys load_phys(int cell, const float* dt, const double* p0, const double* p1, float a_frozen) {
     Phys ph;
     ph.h = __fdiv_rn(*dt, 5.0f);
     ph.a = 0.f;
@@ -31,7 +33,7 @@ __device__ __forceinline__ Phys load_phys(int cell, const float* dt, const doubl
         ph.a = (float)exp(*p0);
         ph.b = (float)(2.0 * exp(*p1));
     } else if (cell == PAIG_CELL_GRAVITY) {
-        ph.a = (float)(exp(*p0) * exp(2.0 * (*p1)));
+        ph.a = a_frozen > 0.f ? a_frozen : (float)(exp(*p0) * exp(2.0 * (*p1)));
     }
     return ph;
 }
@@ -184,10 +186,10 @@ __device__ __forceinline__ void gravity_sub_bwd(const float* P, const Phys& ph, 
 template <int CELL, int NS>   // NS = 2*n_objs
 __global__ void __launch_bounds__(128) rollout_fwd_kernel(int B, int steps, const float* __restrict__ dt,
                                                           const double* __restrict__ p0, const double* __restrict__ p1,
-                                                          float* __restrict__ seq) {
+                                                          float a_frozen, float* __restrict__ seq) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
-    const Phys ph = load_phys(CELL, dt, p0, p1);
+    const Phys ph = load_phys(CELL, dt, p0, p1, a_frozen);
     float* row = seq + (long)b * (steps + 1) * 2 * NS;
     float P[NS], V[NS];
 #pragma unroll
@@ -221,16 +223,18 @@ __global__ void __launch_bounds__(128) rollout_fwd_kernel(int B, int steps, cons
 template <int CELL, int NS>
 __global__ void __launch_bounds__(128) rollout_bwd_kernel(int B, int steps, const float* __restrict__ dt,
                                                           const double* __restrict__ p0, const double* __restrict__ p1,
-                                                          const float* __restrict__ seq, const float* __restrict__ dpos,
+                                                          float a_frozen, const float* __restrict__ seq,
+                                                          const float* __restrict__ dpos,
                                                           const float* __restrict__ dvel, long batch_stride,
                                                           long row_stride, int with_row0, float* __restrict__ d_state0,
-                                                          double* __restrict__ d_phys) {
+                                                          double* d_phys0, double* d_phys1, double* __restrict__ block_part,
+                                                          unsigned* __restrict__ block_count) {
     __shared__ double red[2][4];
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = b < B;
-    const Phys ph = load_phys(CELL, dt, p0, p1);
+    const Phys ph = load_phys(CELL, dt, p0, p1, a_frozen);
     double ga = 0.0, gb = 0.0;
-    if (live) {
+    // a thread walks sequences b, b + grid*block, ... (one sequence per thread unless the caller had no room for
+    // per-block partials and asked for a single block)
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         float gP[NS], gV[NS];
 #pragma unroll
         for (int c = 0; c < NS; ++c) gP[c] = gV[c] = 0.f;
@@ -305,38 +309,60 @@ __global__ void __launch_bounds__(128) rollout_bwd_kernel(int B, int steps, cons
         red[1][w] = gb;
     }
     __syncthreads();
-    if (threadIdx.x == 0 && CELL != PAIG_CELL_BOUNCING && d_phys != nullptr) {
+    if (threadIdx.x == 0 && CELL != PAIG_CELL_BOUNCING && (d_phys0 != nullptr || d_phys1 != nullptr)) {
         double sa = 0.0, sb = 0.0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
             sa += red[0][i];
             sb += red[1][i];
         }
-        atomicAdd(d_phys + 0, sa);      // d_phys is zeroed by the host wrapper; one block => deterministic
-        atomicAdd(d_phys + 1, sb);
+        if (gridDim.x == 1) {
+            if (d_phys0) *d_phys0 = sa;
+            if (d_phys1) *d_phys1 = sb;
+        } else {
+            // several blocks: every block parks its partial, the last one to arrive folds them in block order, so the
+            // result does not depend on which block finishes first (run-to-run bit-identical for any B)
+            block_part[2 * blockIdx.x] = sa;
+            block_part[2 * blockIdx.x + 1] = sb;
+            __threadfence();
+            const unsigned seen = atomicAdd(block_count, 1u);
+            if (seen == gridDim.x - 1) {
+                __threadfence();
+                double ta = 0.0, tb = 0.0;
+                for (unsigned i = 0; i < gridDim.x; ++i) {
+                    ta += ((volatile double*)block_part)[2 * i];
+                    tb += ((volatile double*)block_part)[2 * i + 1];
+                }
+                if (d_phys0) *d_phys0 = ta;
+                if (d_phys1) *d_phys1 = tb;
+            }
+        }
     }
 }
 
 // ---- host wrappers -------------------------------------------------------------------------------
 
 template <int CELL, int NS>
-static void launch_fwd(int B, int steps, const float* dt, const double* p0, const double* p1, float* seq,
+static void launch_fwd(int B, int steps, const float* dt, const double* p0, const double* p1, float aF, float* seq,
                        cudaStream_t st) {
-    launch(rollout_fwd_kernel<CELL, NS>, dim3(cdiv(B, 128)), dim3(128), 0, st, B, steps, dt, p0, p1, seq);
+    launch(rollout_fwd_kernel<CELL, NS>, dim3(cdiv(B, 128)), dim3(128), 0, st, B, steps, dt, p0, p1, aF, seq);
 }
 template <int CELL, int NS>
-static void launch_bwd(int B, int steps, const float* dt, const double* p0, const double* p1, const float* seq,
-                       const float* dpos, const float* dvel, long bs, long rs, int with_row0, float* d0, double* dphys,
-                       cudaStream_t st) {
-    launch(rollout_bwd_kernel<CELL, NS>, dim3(cdiv(B, 128)), dim3(128), 0, st, B, steps, dt, p0, p1, seq, dpos, dvel,
-           bs, rs, with_row0, d0, dphys);
+static void launch_bwd(int B, int steps, const float* dt, const double* p0, const double* p1, float aF, const float* seq,
+                       const float* dpos, const float* dvel, long bs, long rs, int with_row0, float* d0, double* dphys0,
+                       double* dphys1, double* scratch, cudaStream_t st) {
+    // scratch (rollout_scratch_doubles(B) doubles, zero before first use): [0] arrival counter, [2..] per-block partials.
+    // Without it the launch is one block, which needs none.
+    const int blocks = scratch ? cdiv(B, 128) : 1;
+    launch(rollout_bwd_kernel<CELL, NS>, dim3(blocks), dim3(128), 0, st, B, steps, dt, p0, p1, aF, seq, dpos, dvel,
+           bs, rs, with_row0, d0, dphys0, dphys1, scratch ? scratch + 2 : nullptr, reinterpret_cast<unsigned*>(scratch));
 }
 
-int rollout_forward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1, float* seq,
-                    cudaStream_t st) {
+int rollout_forward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1, float aF,
+                    float* seq, cudaStream_t st) {
     if (B <= 0) return 0;
-    if (cell == PAIG_CELL_SPRING && n == 2) launch_fwd<PAIG_CELL_SPRING, 4>(B, steps, dt, p0, p1, seq, st);
-    else if (cell == PAIG_CELL_BOUNCING && n == 2) launch_fwd<PAIG_CELL_BOUNCING, 4>(B, steps, dt, p0, p1, seq, st);
-    else if (cell == PAIG_CELL_GRAVITY && n == 3) launch_fwd<PAIG_CELL_GRAVITY, 6>(B, steps, dt, p0, p1, seq, st);
+    if (cell == PAIG_CELL_SPRING && n == 2) launch_fwd<PAIG_CELL_SPRING, 4>(B, steps, dt, p0, p1, aF, seq, st);
+    else if (cell == PAIG_CELL_BOUNCING && n == 2) launch_fwd<PAIG_CELL_BOUNCING, 4>(B, steps, dt, p0, p1, aF, seq, st);
+    else if (cell == PAIG_CELL_GRAVITY && n == 3) launch_fwd<PAIG_CELL_GRAVITY, 6>(B, steps, dt, p0, p1, aF, seq, st);
     else {
         set_error("rollout: unsupported cell %d with %d objects (reference cells assume 2 / 2 / 3)", cell, n);
         return 1;
@@ -344,17 +370,19 @@ int rollout_forward(int cell, int n, int B, int steps, const float* dt, const do
     return check_launch("rollout_fwd");
 }
 
-int rollout_backward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1,
+int rollout_backward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1, float aF,
                      const float* seq, const float* dpos, const float* dvel, long bs, long rs, int with_row0,
-                     float* d_state0, double* d_phys, cudaStream_t st) {
+                     float* d_state0, double* d_phys0, double* d_phys1, double* scratch, cudaStream_t st) {
     if (B <= 0) return 0;
-    if (d_phys) cudaMemsetAsync(d_phys, 0, 2 * sizeof(double), st);
+    if (B <= 128) scratch = nullptr;                     // one block: no partials, no counter
+    // the arrival counter re-arms itself after every launch, but the caller's workspace starts out uninitialised
+    if (scratch && cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st) != cudaSuccess) return check_launch("rollout_bwd memset");
     if (cell == PAIG_CELL_SPRING && n == 2)
-        launch_bwd<PAIG_CELL_SPRING, 4>(B, steps, dt, p0, p1, seq, dpos, dvel, bs, rs, with_row0, d_state0, d_phys, st);
+        launch_bwd<PAIG_CELL_SPRING, 4>(B, steps, dt, p0, p1, aF, seq, dpos, dvel, bs, rs, with_row0, d_state0, d_phys0, d_phys1, scratch, st);
     else if (cell == PAIG_CELL_BOUNCING && n == 2)
-        launch_bwd<PAIG_CELL_BOUNCING, 4>(B, steps, dt, p0, p1, seq, dpos, dvel, bs, rs, with_row0, d_state0, d_phys, st);
+        launch_bwd<PAIG_CELL_BOUNCING, 4>(B, steps, dt, p0, p1, aF, seq, dpos, dvel, bs, rs, with_row0, d_state0, d_phys0, d_phys1, scratch, st);
     else if (cell == PAIG_CELL_GRAVITY && n == 3)
-        launch_bwd<PAIG_CELL_GRAVITY, 6>(B, steps, dt, p0, p1, seq, dpos, dvel, bs, rs, with_row0, d_state0, d_phys, st);
+        launch_bwd<PAIG_CELL_GRAVITY, 6>(B, steps, dt, p0, p1, aF, seq, dpos, dvel, bs, rs, with_row0, d_state0, d_phys0, d_phys1, scratch, st);
     else {
         set_error("rollout: unsupported cell %d with %d objects", cell, n);
         return 1;

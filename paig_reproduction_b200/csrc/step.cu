@@ -84,7 +84,7 @@ static int forward_common(const paig_task* t, const paig_params* p, const Layout
                               out ? out->enc_masks : nullptr, out ? out->masked_objs : nullptr, ws, st)))
         return rc;
     if ((rc = velocity_forward(t, p, L, ws + L.enc_pos, ws, st))) return rc;
-    if ((rc = rollout_forward(t->cell, d.n, L.B, d.steps, p->dt, p->phys0, p->phys1, ws + L.seq, st))) return rc;
+    if ((rc = rollout_forward(t->cell, d.n, L.B, d.steps, p->dt, p->phys0, p->phys1, t->gravity_A, ws + L.seq, st))) return rc;
     if (out && out->pos_vel_seq)
         cudaMemcpyAsync(out->pos_vel_seq, ws + L.seq, (size_t)L.B * (d.steps + 1) * 4 * d.n * sizeof(float),
                         cudaMemcpyDeviceToDevice, st);
@@ -119,16 +119,14 @@ static int backward_tail(const paig_task* t, const paig_params* p, const paig_pa
                          const float* x, float* ws, cudaStream_t st) {
     const Dims& d = L.d;
     int rc;
-    double* dphys = reinterpret_cast<double*>(ws + L.dphys);
+    // physics-constant gradients go straight to the caller's fp64 slots (spring: k, equil; gravity: g; bouncing: none)
+    double* dphys_scratch = reinterpret_cast<double*>(ws + L.dphys);
     const long rs = 4L * d.n;
-    if ((rc = rollout_backward(t->cell, d.n, L.B, d.steps, p->dt, p->phys0, p->phys1, ws + L.seq, ws + L.d_seq,
-                               ws + L.d_seq + 2 * d.n, (d.steps + 1) * rs, rs, 1, ws + L.d_state0, dphys, st)))
+    if ((rc = rollout_backward(t->cell, d.n, L.B, d.steps, p->dt, p->phys0, p->phys1, t->gravity_A, ws + L.seq, ws + L.d_seq,
+                               ws + L.d_seq + 2 * d.n, (d.steps + 1) * rs, rs, 1, ws + L.d_state0,
+                               t->cell != PAIG_CELL_BOUNCING ? (double*)g->phys0 : nullptr,
+                               t->cell == PAIG_CELL_SPRING ? (double*)g->phys1 : nullptr, dphys_scratch, st)))
         return rc;
-    if (t->cell != PAIG_CELL_BOUNCING) {
-        if (g->phys0) cudaMemcpyAsync(g->phys0, dphys, sizeof(double), cudaMemcpyDeviceToDevice, st);
-        if (t->cell == PAIG_CELL_SPRING && g->phys1)
-            cudaMemcpyAsync(g->phys1, dphys + 1, sizeof(double), cudaMemcpyDeviceToDevice, st);
-    }
     if ((rc = velocity_backward(t, p, g, L, ws + L.d_state0, ws + L.d_enc_pos, ws, st))) return rc;
     if ((rc = encoder_backward(t, p, g, L, x, (long)d.T * d.CHW, d.e, ws + L.d_enc_pos, ws, st))) return rc;
     return templates_backward(t, p, g, ws + L.consts, ws + L.hidden, ws + L.d_consts, ws + L.tmpl_scratch, st);

@@ -12,6 +12,9 @@ There is no CPU path and no PyTorch fallback: tensors must be CUDA tensors and t
 from __future__ import annotations
 
 import ctypes
+import logging
+import os
+import weakref
 from typing import Dict, List, Optional
 
 import numpy as np
@@ -19,16 +22,15 @@ import torch
 import torch.nn as nn
 
 from . import _abi, _lib
+from .base import OPTIMIZERS, BaseNetTorch
+
+logger = logging.getLogger("tf")          # physics_models.py:19 (the reference logs pos_vel_seq rows under this name)
 
 # physics_models.py:31-37
 COORD_UNITS = {"bouncing_balls": 8, "spring_color": 8, "spring_color_half": 8, "3bp_color": 12,
                "mnist_spring_color": 8}
 # cells.py class names accepted by the runner's --cell_type table (runners/torch_run_physics.py:49-75)
 CELLS = {"spring_ode_cell": "spring", "bouncing_ode_cell": "bouncing", "gravity_ode_cell": "gravity"}
-# base.py:12-17
-OPTIMIZERS = {"adam": torch.optim.Adam, "rmsprop": torch.optim.RMSprop, "momentum": lambda p, lr: torch.optim.SGD(p, lr, momentum=0.9),
-              "sgd": torch.optim.SGD}
-
 
 # ---- parameter holders (never executed with torch ops; they exist for state_dict / optimizer parity) ----
 class VariableFromNetwork(nn.Module):
@@ -121,7 +123,7 @@ class _Step(torch.autograd.Function):
         out = net._run_forward(inp, need_backward=need_backward)
         ctx.net = net
         ctx.inp = inp
-        ctx.ws = out.pop("_workspace")
+        ctx.lease = out.pop("_lease")             # returns the workspace to the net's pool when this node dies
         ctx.set_materialize_grads(False)
         ctx.mark_non_differentiable(out["enc_masks"], out["masked_objs"])
         net._last = out
@@ -129,12 +131,31 @@ class _Step(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, d_rec, d_enc_pos, d_seq, _dm, _dmo):
-        grads = ctx.net._run_backward(ctx.inp, ctx.ws, d_out, d_rec, d_enc_pos, d_seq)
+        grads = ctx.net._run_backward(ctx.inp, ctx.lease.ws, d_out, d_rec, d_enc_pos, d_seq)
         return (None, None, None) + tuple(grads)
 
 
-class PhysicsNet(nn.Module):
-    """physics_models.py:40-111.  Same positional constructor as the reference."""
+class _Lease:
+    """A workspace on loan to one autograd node: saved activations live in it between forward and backward.  When the
+    node is released (after backward, or when the graph is dropped) the buffer goes back to the net's pool, so a
+    training loop re-uses ONE workspace instead of allocating ~1 GB per forward."""
+
+    def __init__(self, pool, ws):
+        self.pool, self.ws = pool, ws
+
+    def __del__(self):
+        pool = self.pool() if self.pool is not None else None
+        if pool is not None and len(pool) < 2:
+            pool.append(self.ws)
+
+
+class _Pool(list):
+    pass                                            # a list that can be weakly referenced
+
+
+class PhysicsNet(BaseNetTorch):
+    """physics_models.py:40-111.  Same positional constructor as the reference, same base class surface
+    (paig_reproduction_b200/base.py mirrors nn/network/base.py), so runners/torch_run_physics.py drives it unchanged."""
 
     def __init__(self, task="", recurrent_units=128, lstm_layers=1, cell_type="", seq_len=20, input_steps=3,
                  pred_steps=5, autoencoder_loss=0.0, alt_vel=False, color=False, input_size=36 * 36,
@@ -151,6 +172,7 @@ class PhysicsNet(nn.Module):
         self.device = torch.device(device)
         self.task = task
         self.recurrent_units, self.lstm_layers = recurrent_units, lstm_layers
+        self.cell_type = cell_type
         self.cell_kind = CELLS[cell_type]
         self.seq_len, self.input_steps, self.pred_steps = seq_len, input_steps, pred_steps
         assert seq_len > input_steps + pred_steps and input_steps >= 1 and pred_steps >= 1       # :59,85-86
@@ -165,8 +187,11 @@ class PhysicsNet(nn.Module):
         self.conv_input_shape = [3, side, side]
         self.coord_units = COORD_UNITS[task]
         self.n_objs = self.coord_units // 4
+        self.output_shape = self.conv_input_shape
         self.log_sig = 1.0
-        self.extra_valid_fns, self.extra_test_fns = [], []
+        self.decoder = self.conv_st_decoder                          # physics_models.py:78-80 (looked up by name there)
+        self.extra_valid_fns.append((self.visualize_sequence, [], {}))   # physics_models.py:98-99
+        self.extra_test_fns.append((self.visualize_sequence, [], {}))
         tmpl = side // 2
         # construction order = the reference's (physics_models.py:106-111): same default init under the same seed
         self.var_net_content = VariableFromNetwork([self.n_objs, 3, tmpl, tmpl])
@@ -182,15 +207,23 @@ class PhysicsNet(nn.Module):
         self._unet = "unet" if self.deep else "shallow_unet"
         self._n_convs = 18 if self.deep else 13
         self.batch_global = 0           # set by the data-parallel wrapper: loss normalisers use the job's batch
+        # the reference's gravity cell evaluates A = exp(g) exp(2m) once, in its constructor, so a checkpoint
+        # with g != 0 still rolls out with A = 1 there.  Default here: A follows g (dL/dg flows).  Set
+        # freeze_gravity_A = True to roll out with the constructor-time A like the reference does.
+        self.freeze_gravity_A = False
+        self._gravity_A0 = 1.0          # exp(log 1) * exp(2 log 1): the constructor-time value (cells.py:91-94)
         self._ws_nograd: Dict[int, torch.Tensor] = {}
+        self._ws_pools: Dict[tuple, _Pool] = {}
         self._last: Optional[dict] = None
         self._flat_grad: Optional[torch.Tensor] = None
         self.optimizer = None
 
     # ------------------------------------------------------------------ C-ABI plumbing
     def _task(self, T: int) -> _abi.Task:
+        frozen = self._gravity_A0 if (self.freeze_gravity_A and self.cell_kind == "gravity") else 0.0
         return _abi.Task(_abi.CELL_IDS[self.cell_kind], self.n_objs, self.H, T, self.input_steps, self.pred_steps,
-                         int(self.alt_vel), int(self.deep), float(self.autoencoder_loss), int(self.batch_global))
+                         int(self.alt_vel), int(self.deep), float(self.autoencoder_loss), int(self.batch_global),
+                         float(frozen), 0)
 
     def live_parameter_names(self, with_rollout: bool = True) -> List[str]:
         """state_dict keys that receive a gradient in a LIVE step, in state_dict order."""
@@ -226,7 +259,9 @@ class PhysicsNet(nn.Module):
             raise _lib.PaigError(lib.paig_last_error().decode())
         key = (T, B)
         if fresh:
-            return torch.empty(n // 4 + 64, dtype=torch.float32, device=self.device)
+            pool = self._ws_pools.setdefault(key, _Pool())
+            ws = pool.pop() if pool else torch.empty(n // 4 + 64, dtype=torch.float32, device=self.device)
+            return _Lease(weakref.ref(pool), ws)
         ws = self._ws_nograd.get(key)
         if ws is None:
             ws = self._ws_nograd[key] = torch.empty(n // 4 + 64, dtype=torch.float32, device=self.device)
@@ -246,7 +281,8 @@ class PhysicsNet(nn.Module):
         B, T = x.shape[0], x.shape[1]
         n, H, e, steps = self.n_objs, self.H, self.input_steps + self.pred_steps, T - self.input_steps
         dev = self.device
-        ws = self._workspace(T, B, fresh=need_backward)
+        lease = self._workspace(T, B, fresh=True) if need_backward else _Lease(None, self._workspace(T, B, fresh=False))
+        ws = lease.ws
         out = dict(output_seq=torch.empty(B, steps, 3, H, H, device=dev), recons_out=torch.empty(B, e, 3, H, H, device=dev),
                    enc_pos=torch.empty(B, e, 2 * n, device=dev), pos_vel_seq=torch.empty(B, steps + 1, 4 * n, device=dev),
                    enc_masks=torch.empty(B * e, n + 1, H, H, device=dev),
@@ -260,7 +296,7 @@ class PhysicsNet(nn.Module):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.paig_step_forward(ctypes.byref(tk), ctypes.byref(P), x.data_ptr(), B, ctypes.byref(O),
                                          ws.data_ptr(), stream), "paig_step_forward")
-        out["_workspace"] = ws
+        out["_lease"] = lease
         out["_x"] = x
         return out
 
@@ -271,6 +307,9 @@ class PhysicsNet(nn.Module):
         with_rollout = d_out is not None or d_seq is not None
         live = self.live_parameter_names(with_rollout=True)
         params = self._params_now()
+        if self.input_steps == 1:
+            # physics_models.py:222-223: vel = zeros, the velocity encoder is not on the graph -> grad stays None
+            live = [k for k in live if not k.startswith("velocity_encoder.")]
         grads = {k: torch.empty_like(params[k]) for k in live}
         P, G = self._param_table(params), self._param_table(grads)
         tk = self._task(T)
@@ -311,7 +350,77 @@ class PhysicsNet(nn.Module):
         self.contents = raw[n * t * t:4 * n * t * t].view(n, 3, t, t)
         self.background_content = torch.sigmoid(raw[4 * n * t * t:].view(1, 3, H, H))
         self.step_losses = last["losses"]          # [train, pred, extrap, recons] reduced in-kernel (no autograd)
+        self._layers = None                        # transf_contents / transf_masks of the last decoder call, on demand
+        self._last_decode_loc = pos_vel_seq.detach()[:, -1, :2 * n]
         return output_seq
+
+    # ---- the decoder as a method (physics_models.py:78-80,151-199) and the per-layer tensors it caches ----
+    def _decoder_constants(self):
+        """paig_templates_forward: raw VariableFromNetwork outputs and [template+5 | sigmoid(contents) | sigmoid(bg)]."""
+        lib = _lib.load()
+        n, t, H = self.n_objs, self.H // 2, self.H
+        CN = n * t * t * 4 + 3 * H * H
+        raw = torch.empty(CN, device=self.device)
+        consts = torch.empty(CN, device=self.device)
+        hidden = torch.empty(3 * 200, device=self.device)
+        tk, P = self._task(self.seq_len), self._param_table(self._params_now())
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(lib.paig_templates_forward(ctypes.byref(tk), ctypes.byref(P), raw.data_ptr(), consts.data_ptr(),
+                                              hidden.data_ptr(), stream), "paig_templates_forward")
+        return raw, consts
+
+    def conv_st_decoder(self, inp):
+        """physics_models.py:151-199 for positions ``inp`` [N, 2n] -> frames [N, 3, H, H] (no autograd through this
+        stand-alone call; inside ``forward`` the decoder runs -- and is differentiated -- within the fused step)."""
+        lib = _lib.load()
+        if not inp.is_cuda:
+            raise _lib.PaigError("conv_st_decoder needs CUDA tensors: there is no CPU fallback")
+        loc = inp.detach().contiguous().float()
+        N, n, t, H = loc.shape[0], self.n_objs, self.H // 2, self.H
+        raw, consts = self._decoder_constants()
+        self.template = raw[:n * t * t].view(n, 1, t, t)
+        self.contents = raw[n * t * t:4 * n * t * t].view(n, 3, t, t)
+        self.background_content = consts[4 * n * t * t:].view(1, 3, H, H)
+        frames = torch.empty(N, 3, H, H, device=self.device)
+        tk = self._task(self.seq_len)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(lib.paig_decode_forward(ctypes.byref(tk), consts.data_ptr(), loc.data_ptr(), N, frames.data_ptr(), None, 0,
+                                           1, None, stream), "paig_decode_forward")
+        self._layers = None
+        self._last_decode_loc = loc
+        return frames
+
+    def _decode_layers(self):
+        if getattr(self, "_layers", None) is None:
+            lib = _lib.load()
+            loc = self._last_decode_loc.contiguous().float()
+            N, n, H = loc.shape[0], self.n_objs, self.H
+            _, consts = self._decoder_constants()
+            tc = torch.empty(n + 1, N, 3, H, H, device=self.device)
+            tm = torch.empty(n + 1, N, 3, H, H, device=self.device)
+            tk = self._task(self.seq_len)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(lib.paig_decode_layers(ctypes.byref(tk), consts.data_ptr(), loc.data_ptr(), N, tc.data_ptr(),
+                                              tm.data_ptr(), stream), "paig_decode_layers")
+            self._layers = (tc, tm)
+        return self._layers
+
+    @property
+    def transf_contents(self):
+        """physics_models.py:190: list of n+1 tensors [N,3,H,H] of the LAST decoder call (the final rollout step):
+        each object's sampled sigmoid(content), then the tiled background.  Materialised on first access."""
+        return list(self._decode_layers()[0].unbind(0))
+
+    @property
+    def transf_masks(self):
+        """physics_models.py:192-196: tuple of n+1 softmax masks [N,3,H,H] of the last decoder call."""
+        return tuple(self._decode_layers()[1].unbind(0))
+
+    def visualize_sequence(self):
+        """physics_models.py:247-330 (registered as extra valid / test fn, :98-99): example%d.jpg, animation%d.gif,
+        templates.jpg and extra_outputs.npz in save_dir."""
+        from .viz import visualize_sequence
+        return visualize_sequence(self, logger)
 
     def compute_loss(self):                                           # physics_models.py:119-142
         from .losses import frame_sse

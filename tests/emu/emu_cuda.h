@@ -109,6 +109,7 @@ static inline T __shfl_up_sync(unsigned, T v, unsigned d, int width = 32) {
 template <typename T>
 static inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }   // fibers: one host thread
 static inline float atomicExch(float* p, float v) { float o = *p; *p = v; return o; }
+static inline void __threadfence() {}                                            // one host thread: nothing to order
 
 static inline int min(int a, int b) { return a < b ? a : b; }
 static inline int max(int a, int b) { return a > b ? a : b; }
