@@ -73,27 +73,53 @@ class ClockSampler(threading.Thread):
 
 
 def cpu_leg(steps, warmup, budget_s=25.0):
-    """The oracle LIVE step on all host threads; returns (seq/s, cores, sample description, seconds per step)."""
+    """The reference's own LIVE step (net.output = net(x); compute_loss(); backward()) on all host threads, through its
+    public API, from the ignored copy oracle/_ref/reference (oracle/fetch_reference.py); when that copy is absent, the
+    oracle port.  Returns (seq/s, cores, sample description, seconds per step, kind)."""
     import torch
 
+    from oracle import fetch_reference
     from oracle import physicsnet_oracle as po
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     spec = po.TASKS[TASK]
     sd = po.init_state_dict(spec, 0)
     x = po.synthetic_frames(spec, B_PER_GPU, spec.seq_len, 0)
+    kind = "port"
+    if fetch_reference.reference_path() is not None:
+        try:
+            pm = fetch_reference.import_reference()
+            net = pm.PhysicsNet(TASK, 100, 1, "spring_ode_cell", spec.seq_len, spec.input_steps, spec.pred_steps, ALPHA,
+                                False, True, spec.H * spec.H, "conv_encoder", "conv_st_decoder")
+            net.load_state_dict(sd, strict=True)
+            kind = "reference"
+        except Exception as e:                      # e.g. a dependency of the reference missing on this box
+            sys.stderr.write("bench: reference import failed (%s: %s); timing the oracle port\n" % (type(e).__name__, e))
+
+    def one_step():
+        if kind == "reference":
+            net.zero_grad(set_to_none=True)
+            inp = x.clone().requires_grad_(True)    # base.py:141
+            net.output = net(inp)                   # LIVE (SURVEY Q1): what base.py:195 does in eval
+            loss, _ = net.compute_loss()
+            loss.backward()
+        else:
+            po.live_step(sd, x, spec, ALPHA)
+
     times = []
     t_start = time.perf_counter()
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        po.live_step(sd, x, spec, ALPHA)
+        one_step()
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
         if time.perf_counter() - t_start > budget_s and len(times) >= 2:
             break
     med = statistics.median(times)
-    return B_PER_GPU / med, cores, "%d timed LIVE steps of %s B=%d (median), %d warm-up" % (len(times), TASK, B_PER_GPU, warmup), med
+    what = "the unmodified reference (oracle/_ref)" if kind == "reference" else "the oracle port"
+    return (B_PER_GPU / med, cores, "%d timed LIVE steps of %s B=%d through %s (median), %d warm-up"
+            % (len(times), TASK, B_PER_GPU, what, warmup), med, kind)
 
 
 def reference_arm(args):
@@ -101,15 +127,17 @@ def reference_arm(args):
     if rank != 0:
         return
     steps = max(2, min(args.steps, 8))
-    val, cores, sample, med = cpu_leg(steps, max(1, min(args.warmup, 2)), budget_s=90.0)
+    val, cores, sample, med, kind = cpu_leg(steps, max(1, min(args.warmup, 2)), budget_s=90.0)
     line = {"impl": "reference", "metric": "train sequences/sec (fwd+bwd, spring_color, bs=100)", "value": val,
             "unit": "sequences/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, min(args.warmup, 2)),
             "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": "spring_color PhysicsNet LIVE step (fwd+bwd), batch 100, CPU", "task": TASK,
-                       "batch": B_PER_GPU, "note": "pure-Python reference cannot travel to the GPU box; this is its pinned CPU "
-                                                   "restatement (oracle/physicsnet_oracle.py) on all host threads"},
-            "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": {"workload": "spring_color PhysicsNet LIVE training step (fwd+bwd, all parameter gradients), "
+                                   "2 objects, 32x32 RGB, T=12, batch 100, on the host CPU", "task": TASK,
+                       "batch": B_PER_GPU, "note": "the reference's own PhysicsNet through its public API "
+                                                   "(net(x); compute_loss(); backward()) on all host threads"
+                       if kind == "reference" else "oracle port (reference copy absent on this box)"},
+            "cpu_baseline": {"value": val, "unit": "sequences/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "sequences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -122,7 +150,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sustained / drop-in / strong-scaling extra keys")
     args = ap.parse_args()
+    import warnings
+    warnings.filterwarnings("ignore")
     if args.impl == "reference":
         return reference_arm(args)
     args.warmup = max(args.warmup, 3)
@@ -231,6 +262,74 @@ def main():
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    extras = {}
+    if not args.no_extras:
+        # (1) sustained: the same step for >= 2 s back to back (the headline region is a ~0.1 s burst)
+        n_sus = max(args.steps, int(2.2e3 / max(ms_total / args.steps, 1e-3)))
+        barrier()
+        e0.record(stream)
+        for i in range(n_sus):
+            step(i)
+        e1.record(stream)
+        barrier()
+        ms_sus = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_sus, op=dist.ReduceOp.MAX)
+        extras["sustained"] = {"steps": n_sus, "seconds": float(ms_sus.item()) * 1e-3,
+                               "value": B_PER_GPU * world * n_sus / (float(ms_sus.item()) * 1e-3), "unit": "sequences/s"}
+        # (2) the reference's own call sequence on the drop-in module (what base.py:142-151 / :195 does):
+        #     net.output = net(inp); loss, _ = net.compute_loss(); loss.backward()  -- frames materialised, torch autograd
+        def dropin_step(i):
+            inp = dev_pool[i % POOL].requires_grad_(True)
+            net.output = net(inp)
+            loss, _ = net.compute_loss()
+            for p_ in net.parameters():
+                p_.grad = None
+            loss.backward()
+        for i in range(3 if world == 1 else 0):
+            dropin_step(i)
+        barrier()
+        n_drop = max(5, min(args.steps, 20))
+        e0.record(stream)
+        for i in range(n_drop if world == 1 else 0):
+            dropin_step(i)
+        e1.record(stream)
+        barrier()
+        ms_drop = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world == 1:
+            extras["dropin_module_path"] = {"value": B_PER_GPU * world * n_drop / (float(ms_drop.item()) * 1e-3), "unit": "sequences/s",
+                                        "ms_per_step": float(ms_drop.item()) / n_drop,
+                                            "api": "net.output = net(inp); net.compute_loss(); loss.backward() (paig_step_forward "
+                                                   "+ paig_frame_sse_* + paig_step_backward under torch autograd), 1 GPU"}
+        for p_ in net.parameters():
+            p_.grad = None
+        net._flat_grad = None
+        flat = net.flat_gradients()
+        # (3) strong scaling: BASELINE config 3's reading of "batch 100 on N GPUs" -- the GLOBAL batch stays 100
+        if world > 1:
+            from paig_reproduction_b200.parallel import shard_bounds
+            lo, hi = shard_bounds(B_PER_GPU, world, rank)
+            net.batch_global = B_PER_GPU
+            shard = [d_[lo:hi].contiguous() for d_ in dev_pool]
+
+            def strong_step(i):
+                net.train_step(shard[i % POOL])
+                allreduce_step(flat, net._phys_grad)
+            for i in range(args.warmup):
+                strong_step(i)
+            barrier()
+            e0.record(stream)
+            for i in range(args.steps):
+                strong_step(i)
+            e1.record(stream)
+            barrier()
+            ms_st = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            dist.all_reduce(ms_st, op=dist.ReduceOp.MAX)
+            extras["strong_scaling"] = {"global_batch": B_PER_GPU, "sequences_per_rank": "%d-%d" % (B_PER_GPU // world, -(-B_PER_GPU // world)),
+                                        "value": B_PER_GPU * args.steps / (float(ms_st.item()) * 1e-3), "unit": "sequences/s",
+                                        "ms_per_step": float(ms_st.item()) / args.steps}
+            net.batch_global = B_PER_GPU * world
+
     # ---- live per-kernel timing (separate instrumented pass right after the timed region; events between launches
     #      would otherwise perturb the headline number) ----
     prof_steps = min(args.steps, 10)
@@ -303,9 +402,10 @@ def main():
                 "kernels_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in sorted(kern.items(), key=lambda kv: -kv[1]["ms_per_step"])},
                 "sgemm_parts_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in parts.items()},
                 "losses": losses}
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
-            val, cores, sample, _ = cpu_leg(6, 1)
-            line["cpu_baseline"] = {"value": val, "unit": "sequences/s", "cores": cores, "kind": "port", "sample": sample}
+            val, cores, sample, _, kind = cpu_leg(6, 1)
+            line["cpu_baseline"] = {"value": val, "unit": "sequences/s", "cores": cores, "kind": kind, "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

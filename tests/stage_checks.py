@@ -293,9 +293,13 @@ def kink_flips(force, sd, x, spec):
 
 
 def check_step(be, task, B, seed=0, alpha=3.0, alt_vel=False, seq_len=None, tol=1e-4, batch_global=0, fwd_tol=2e-5,
-               traj_tol=5e-5, report=None, phys=None):
-    """LIVE training step: paig_step_fused, then paig_step_forward + paig_step_backward, vs the oracle."""
+               traj_tol=5e-5, report=None, phys=None, horizon=None):
+    """LIVE training step: paig_step_fused, then paig_step_forward + paig_step_backward, vs the oracle.
+    horizon = (pred_steps, seq_len) shortens the rollout (the constructor accepts any in/pr/seq_len, physics_models.py:41-55):
+    used where a long chaotic rollout would bury the comparison under the reference's own fp32 noise."""
     spec = po.TASKS[task]
+    if horizon is not None:
+        spec = po.TaskSpec(spec.task, spec.cell, horizon[1], spec.test_seq_len, spec.input_steps, horizon[0], spec.H, spec.n_objs)
     T = seq_len or spec.seq_len
     sd = po.init_state_dict(spec, seed, alt_vel, phys=phys)
     x = po.synthetic_frames(spec, B, T, seed)

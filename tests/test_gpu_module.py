@@ -247,3 +247,73 @@ def test_fused_unet_kernels_are_the_path_taken(task, max_launches):
     torch.cuda.synchronize()
     n = lib.paig_launch_count() - n0
     assert 0 < n <= max_launches, "%d launches in one %s step" % (n, task)
+
+
+@pytest.mark.parametrize("task,B", [("spring_color", 260), ("3bp_color", 140), ("mnist_spring_color", 12)])
+def test_training_step_is_bit_reproducible(task, B):
+    """Every reduction of the step runs in a fixed order -- also the decoder backward at 64 px (row-banded gather, no
+    float atomics) and the rollout backward's fp64 sums when B spans several blocks (> 128 sequences)."""
+    spec = po.TASKS[task]
+    net = _net(task, spec.seq_len, 3.0)
+    net.load_state_dict(po.init_state_dict(spec, 0), strict=True)
+    x = po.synthetic_frames(spec, B, spec.seq_len, 31).to(DEV)
+    runs = []
+    for _ in range(3):
+        losses = net.train_step(x).clone()
+        torch.cuda.synchronize()
+        runs.append((losses, net.flat_gradients().detach().clone(), net._phys_grad.detach().clone()))
+    for losses, flat, phys in runs[1:]:
+        assert torch.equal(losses, runs[0][0]) and torch.equal(flat, runs[0][1]) and torch.equal(phys, runs[0][2])
+    assert torch.isfinite(runs[0][1]).all()
+    if task != "mnist_spring_color":
+        assert runs[0][2].abs().max().item() > 0          # the physics gradients are live (k / equil / g)
+
+
+def test_gravity_A_follows_g_unless_frozen_like_the_reference():
+    """SURVEY Q3.  The reference's gravity cell computes A = exp(g) exp(2m) once in its constructor (cells.py:92-94),
+    so after load_state_dict with g != 0 it still integrates with the constructor-time A = 1.  Default here: A follows
+    g (the oracle with A refreshed); freeze_gravity_A = True reproduces the reference's frozen value."""
+    spec = po.TASKS["3bp_color"]
+    sd = po.init_state_dict(spec, 0, phys={"g": 0.3})
+    x = po.synthetic_frames(spec, 3, spec.seq_len, 5)
+    live = po.feedforward(sd, x, spec)["pos_vel_seq"]
+    sd_frozen = dict(sd)
+    sd_frozen["rollout_cell.g"] = torch.tensor(0.0, dtype=torch.float64)      # A = exp(0) exp(0) = 1 whatever the checkpoint says
+    frozen = po.feedforward(sd_frozen, x, spec)["pos_vel_seq"]
+    assert (live - frozen).abs().max() / live.abs().max() > 2e-2          # the two behaviours are far apart ...
+    net = _net("3bp_color", spec.seq_len, 5.0)
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        net(x.to(DEV))
+        _close(net.pos_vel_seq.cpu().numpy(), live.numpy(), 1e-3)           # ... and each is matched 20x closer than that
+        net.freeze_gravity_A = True
+        net(x.to(DEV))
+        _close(net.pos_vel_seq.cpu().numpy(), frozen.numpy(), 1e-3)
+
+
+@pytest.mark.parametrize("task", ["spring_color", "3bp_color", "mnist_spring_color"])
+def test_transf_layers_and_decoder_method(task):
+    """physics_models.py:190,196: transf_contents / transf_masks of the last decoder call (the final rollout step), and
+    the decoder as a bound method (:78-80) -- against the oracle's decoder with its intermediates exposed."""
+    spec = po.TASKS[task]
+    B = 3
+    sd = po.init_state_dict(spec, 1)
+    x = po.synthetic_frames(spec, B, spec.seq_len, 2)
+    net = _net(task, spec.seq_len, 3.0)
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out = net(x.to(DEV))
+    loc = net.pos_vel_seq[:, -1, :2 * spec.n_objs].cpu()
+    extras = {}
+    ref = po.decoder(sd, loc, spec, extras=extras)
+    tc, tm = net.transf_contents, net.transf_masks
+    assert isinstance(tc, list) and isinstance(tm, tuple) and len(tc) == len(tm) == spec.n_objs + 1
+    for o in range(spec.n_objs + 1):
+        assert tuple(tc[o].shape) == tuple(tm[o].shape) == (B, 3, spec.H, spec.H)
+        _close(tc[o].cpu().numpy(), extras["transf_contents"][o].numpy(), 2e-5)
+        _close(tm[o].cpu().numpy(), extras["transf_masks"][o].numpy(), 2e-5)
+    comp = sum(m * c for m, c in zip(tm, tc))
+    _close(comp.cpu().numpy(), out[:, -1].cpu().numpy(), 2e-6)         # the composite of the layers is the decoded frame
+    frames = net.decoder(loc.to(DEV))
+    _close(frames.cpu().numpy(), ref.numpy(), 2e-5)
+    assert torch.equal(frames, out[:, -1])
