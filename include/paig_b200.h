@@ -226,6 +226,13 @@ int paig_profile_end(char* buf, size_t cap);
 int paig_debug_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int fixed_split, float* scratch,
                        long scratch_floats, void* stream);
 
+/* Test hook: the tcgen05 implicit-GEMM convolution (csrc/conv_tc.cu) on its own.  x [N,Cin,S,S] -> y [N,Cout,S,S];
+ * w: [Cout][Cin][3][3], or with transposed != 0 the layer weight [Cin][Cout][3][3] applied with flipped taps (the data
+ * gradient of blocks.py's Conv2d).  scratch: 9*Cin*Cout floats.  Fails when the shape does not qualify
+ * (Cin % 8, Cout in {16,32,48,64,96,128}, S in {8,16,32,64}). */
+int paig_debug_conv3x3_tc(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout, int S,
+                          int relu, int transposed, float* scratch, void* stream);
+
 /* Test hook: offset (in floats) of a named workspace region ("act", "grad" with a UNet buffer index; "logits",
  * "d_logits", "enc_pos", "d_enc_pos", "seq", "d_seq", "d_consts", "consts", "A", "dA"), or -1. */
 long paig_debug_workspace_offset(const paig_task* t, int B, const char* region, int index);

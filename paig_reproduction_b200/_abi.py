@@ -109,6 +109,7 @@ def declare(lib):
         "paig_optimizer_step_f64": (i, [i, vp, vp, vp, vp, l, C.c_double, i, vp]),
         "paig_gather_batch_u8": (i, [vp, l, vp, i, vp, vp]),
         "paig_debug_gemm_tc": (i, [vp, vp, vp, i, i, i, i, vp, l, vp]),
+        "paig_debug_conv3x3_tc": (i, [vp, vp, vp, vp, i, i, i, i, i, i, vp, vp]),
         "paig_stage_input_host": (i, [PT, vp, i, i, vp, vp]),
         "paig_step_fused_staged": (i, [PT, PP, PP, i, i, vp, vp, vp]),
     }
@@ -130,5 +131,5 @@ EXPORTS = ["paig_abi_version", "paig_last_error", "paig_workspace_bytes", "paig_
            "paig_encoder_forward", "paig_encoder_backward", "paig_velocity_forward", "paig_velocity_backward",
            "paig_conv3x3_forward", "paig_conv3x3_backward", "paig_debug_workspace_offset", "paig_debug_unet_conv_view",
            "paig_frame_sse_forward", "paig_frame_sse_backward", "paig_launch_count", "paig_profile_begin",
-           "paig_profile_end", "paig_optimizer_step", "paig_optimizer_step_f64", "paig_gather_batch_u8", "paig_debug_gemm_tc", "paig_stage_input_host",
+           "paig_profile_end", "paig_optimizer_step", "paig_optimizer_step_f64", "paig_gather_batch_u8", "paig_debug_gemm_tc", "paig_debug_conv3x3_tc", "paig_stage_input_host",
            "paig_step_fused_staged"]

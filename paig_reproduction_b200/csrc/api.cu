@@ -225,6 +225,18 @@ int paig_decode_backward(const paig_task* t, const float* consts, const float* l
     return decode_run(t, consts, a, b, true, (float*)workspace, d_consts, 1, (cudaStream_t)stream);
 }
 
+int paig_debug_conv3x3_tc(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout, int S, int relu,
+                          int transposed, float* scratch, void* stream) {
+    ConvArgs a;
+    a.in = x; a.in_bs = (long)Cin * S * S; a.Cin = Cin;
+    a.w = w; a.b = b;
+    a.out = y; a.out_bs = (long)Cout * S * S; a.Cout = Cout;
+    a.S = S; a.N = N; a.relu = relu; a.transposed = transposed;
+    const int rc = conv3x3_tc(a, scratch, (cudaStream_t)stream);
+    if (rc < 0) { set_error("conv3x3_tc: %d -> %d channels at %d px does not qualify (or tcgen05 is switched off)", Cin, Cout, S); return 1; }
+    return rc;
+}
+
 int paig_conv3x3_forward(const float* x, const float* w, const float* b, float* y, int N, int Cin, int Cout, int S,
                          int relu, void* stream) {
     ConvArgs a;

@@ -389,6 +389,10 @@ static void conv_geometry(int S, int N, int* QX, int* TH, int* FPB, int* strips)
 int conv3x3(const ConvArgs& in_args, cudaStream_t st) {
     ConvArgs a = in_args;
     if (a.N <= 0) return 0;
+    if (a.tc_scratch) {               // dense layers (channels in multiples of 8 / 16): 3xTF32 implicit GEMM on tcgen05
+        const int rc = conv3x3_tc(a, a.tc_scratch, st);
+        if (rc >= 0) return rc;
+    }
     int strips;
     conv_geometry(a.S, a.N, &a.QX, &a.TH, &a.FPB, &strips);
     // the frame groups ride on grid.z (<= 65535): very large batches (the 8192-sequence evaluation sweep is 81 920

@@ -178,6 +178,16 @@ Layout make_layout(const paig_task* t, int B) {
     L.partials = take(max_w);
     L.partials_floats = max_w;
     L.tc_scratch = take((size_t)L.K * kHidden + (size_t)kHidden * nN + (size_t)L.K * nN);
+    {
+        size_t mx = 64;
+        if (t->deep_unet)
+            for (int i = 0; i < L.unet.nops; ++i)
+                if (L.unet.ops[i].kind == OP_CONV) {
+                    const size_t w = conv_tc_scratch_floats(L.unet.ops[i].in.C, L.unet.ops[i].out.C);
+                    mx = w > mx ? w : mx;
+                }
+        L.convtc = take(mx);
+    }
     L.wpack = take(unet_wpack_floats(L.unet, t));
     L.frames = take(N * d.CHW);
     L.x_stage = take((size_t)B * d.T * d.CHW);
@@ -223,6 +233,7 @@ static int unet_forward(const paig_task* t, const paig_params* p, const Layout& 
             a.w = p->conv[op.layer].w; a.b = p->conv[op.layer].b;
             a.out = o.p; a.out_bs = o.bs; a.Cout = op.out.C;
             a.N = L.N; a.relu = op.relu;
+            a.tc_scratch = t->deep_unet ? ws + L.convtc : nullptr;
             rc = conv3x3(a, st);
         } else if (op.kind == OP_POOL) {
             View v = view_of(L, ws, op.in, false), o = view_of(L, ws, op.out, false);
@@ -316,6 +327,7 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
                 a.w = p->conv[op.layer].w; a.transposed = 1;
                 a.out = gi.p; a.out_bs = gi.bs; a.Cout = op.in.C;
                 a.S = o.S; a.N = L.N;
+                a.tc_scratch = t->deep_unet ? ws + L.convtc : nullptr;
                 rc = conv3x3(a, st);
             }
         } else if (op.kind == OP_POOL) {

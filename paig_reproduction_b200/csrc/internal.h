@@ -53,9 +53,14 @@ struct ConvArgs {
     float* out = nullptr; long out_bs = 0; int Cout = 0;
     int S = 0, N = 0;
     int relu = 0, transposed = 0;
+    float* tc_scratch = nullptr;                       // nullable: 9*Cin*Cout floats; lets conv3x3() take the tcgen05 path
     int QX = 0, TH = 0, FPB = 0, CK = 0;               // filled by conv3x3()
 };
 int conv3x3(const ConvArgs& a, cudaStream_t st);
+// conv_tc.cu: tcgen05 3xTF32 implicit GEMM; -1 when the layer does not qualify.  scratch: conv_tc_scratch_floats() floats.
+int conv3x3_tc(const ConvArgs& a, float* scratch, cudaStream_t st);
+size_t conv_tc_scratch_floats(int Cin, int Cout);
+bool conv_tc_enabled();
 constexpr int kWgradMaxCtas = 296;
 // Deferred fixed-order reductions of per-CTA partials: the weight-gradient kernels of a whole backward pass queue
 // their (partials -> dW, db) folds here and one launch performs them all.

@@ -48,6 +48,7 @@ struct Layout {
     size_t partials;             // conv wgrad / head partial sums; split-K partials of the MLP GEMMs
     size_t partials_floats;
     size_t tc_scratch;           // transposed operands of the tcgen05 encoder.l1 GEMMs: W1^T | dH1^T | A^T
+    size_t convtc;               // packed weights of the layer in flight on the tcgen05 conv path (deep UNet)
     size_t wpack;                // UNet weights re-packed [ci][tap][co]|bias for the fused forward kernel
     size_t frames;               // gathered encoder frames [N,3,H,H] (when they are a prefix of each sequence)
     size_t x_stage;              // device copy of the input for the *_host entry points (slot 0)
