@@ -231,7 +231,7 @@ int paig_debug_conv3x3_tc(const float* x, const float* w, const float* b, float*
     a.in = x; a.in_bs = (long)Cin * S * S; a.Cin = Cin;
     a.w = w; a.b = b;
     a.out = y; a.out_bs = (long)Cout * S * S; a.Cout = Cout;
-    a.S = S; a.N = N; a.relu = relu; a.transposed = transposed;
+    a.S = S; a.N = N; a.relu = relu; a.transposed = transposed; a.force_tc = 1;
     const int rc = conv3x3_tc(a, scratch, (cudaStream_t)stream);
     if (rc < 0) { set_error("conv3x3_tc: %d -> %d channels at %d px does not qualify (or tcgen05 is switched off)", Cin, Cout, S); return 1; }
     return rc;

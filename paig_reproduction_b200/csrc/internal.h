@@ -54,6 +54,7 @@ struct ConvArgs {
     int S = 0, N = 0;
     int relu = 0, transposed = 0;
     float* tc_scratch = nullptr;                       // nullable: 9*Cin*Cout floats; lets conv3x3() take the tcgen05 path
+    int force_tc = 0;                                  // test hook: skip the profitability rule of conv3x3_tc()
     int QX = 0, TH = 0, FPB = 0, CK = 0;               // filled by conv3x3()
 };
 int conv3x3(const ConvArgs& a, cudaStream_t st);
