@@ -111,6 +111,13 @@ int paig_step_backward(const paig_task* t, const paig_params* p, const paig_para
 int paig_step_fused(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x, int B,
                     const paig_outputs* out, void* workspace, void* stream);
 
+/* Data-parallel overlap hook: arm a cudaEvent_t (passed as void*) that the NEXT paig_step_fused* call on this thread
+ * records as soon as every gradient except the UNet conv layers' (encoder.{shallow_unet,unet}.c*) is final -- that is
+ * before the UNet backward, ~half of the step.  The caller makes a side stream wait for the event and all-reduces that
+ * part of its flat gradient buffer there while the UNet backward runs (paig_reproduction_b200/parallel.py).  The
+ * reference has no distributed code; SURVEY 8(e). */
+void paig_set_early_grad_event(void* cuda_event);
+
 /* Same as paig_step_fused but with HOST buffers: x_host (pinned or pageable) is copied to the device
  * staging area inside the workspace, and the four losses are copied back to losses_host.  This is the
  * end-to-end call bench.py times as `e2e`. */

@@ -85,6 +85,7 @@ def declare(lib):
         "paig_step_backward": (i, [PT, PP, PP, vp, i, vp, vp, vp, vp, vp, vp]),
         "paig_step_fused": (i, [PT, PP, PP, vp, i, PO, vp, vp]),
         "paig_step_fused_host": (i, [PT, PP, PP, vp, i, vp, vp, vp]),
+        "paig_set_early_grad_event": (None, [vp]),
         "paig_rollout_forward": (i, [i, i, i, i, vp, vp, vp, vp, vp]),
         "paig_rollout_backward": (i, [i, i, i, i, vp, vp, vp, vp, vp, vp, vp, vp]),
         "paig_templates_forward": (i, [PT, PP, vp, vp, vp, vp]),
@@ -126,7 +127,7 @@ def declare(lib):
 
 
 EXPORTS = ["paig_abi_version", "paig_last_error", "paig_workspace_bytes", "paig_step_forward", "paig_step_backward",
-           "paig_step_fused", "paig_step_fused_host", "paig_rollout_forward", "paig_rollout_backward",
+           "paig_step_fused", "paig_step_fused_host", "paig_set_early_grad_event", "paig_rollout_forward", "paig_rollout_backward",
            "paig_templates_forward", "paig_templates_backward", "paig_decode_forward", "paig_decode_backward", "paig_decode_layers",
            "paig_encoder_forward", "paig_encoder_backward", "paig_velocity_forward", "paig_velocity_backward",
            "paig_conv3x3_forward", "paig_conv3x3_backward", "paig_debug_workspace_offset", "paig_debug_unet_conv_view",

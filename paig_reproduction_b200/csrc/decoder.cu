@@ -99,9 +99,11 @@ decode_kernel(int H, int band_rows, const float* __restrict__ consts, DecSeg seg
         const float* tgt = sg.target ? sg.target + (long)q * sg.tgt_seq_stride + (long)r * 3 * HW : nullptr;
         float* frame = sg.frames ? sg.frames + (long)fl * 3 * HW : nullptr;
         const float* dfr = sg.dframes ? sg.dframes + (long)fl * 3 * HW : nullptr;
-        const float gscale = (BWD && sg.scale) ? 2.f * sg.scale[r] : 0.f;
+        const bool has_scale = sg.scale != nullptr || sg.use_scale != 0;
+        const float srow = sg.scale ? sg.scale[r] : (r < sg.scale_split ? sg.scale_lo : sg.scale_hi);
+        const float gscale = (BWD && has_scale) ? 2.f * srow : 0.f;
         // a frame needs the backward math only if some gradient reaches it
-        const bool do_bwd = BWD && (dfr != nullptr || (sg.scale != nullptr && gscale != 0.f));
+        const bool do_bwd = BWD && (dfr != nullptr || (has_scale && gscale != 0.f));
 
         for (int k = tid; k < 2 * NOBJ * H; k += kDecThreads) {
             const int axis = k / (NOBJ * H), o = (k / H) % NOBJ, p = k % H;

@@ -127,12 +127,20 @@ Layout make_layout(const paig_task* t, int B) {
         return o;
     };
     const size_t N = (size_t)L.N, nN = (size_t)d.n * L.N, nB = (size_t)d.n * B;
+    // PAIG_FLAG_INFERENCE (forward only: eval_performance, base.py:174-218): nothing is kept for a backward pass.  With
+    // the ShallowUNet the fused forward kernel then stores no activation at all, and every gradient / staging region
+    // has size zero: ~0.65 MB per sequence instead of ~14.5 MB (spring_color_half test mode), so the 8192-sequence
+    // evaluation sweep needs ~5 GB, not 119 GB.
+    const bool inf = (t->flags & PAIG_FLAG_INFERENCE) != 0;
+    static const bool layerwise = getenv("PAIG_UNET_LAYERWISE") != nullptr;
+    const bool acts_on_chip = inf && !t->deep_unet && !layerwise && d.H <= 36;
+    auto bwd = [&](size_t floats) { return inf ? (size_t)0 : floats; };     // regions only a backward pass touches
     size_t max_w = 0, sum_w = 0;
     for (int i = 0; i < L.unet.nbufs; ++i) {
         const int S = d.H >> L.unet.bufs[i].shift;
         const size_t fl = N * L.unet.bufs[i].C * S * S;
-        L.act[i] = take(fl);
-        L.grad[i] = take(fl);
+        L.act[i] = take(acts_on_chip ? 0 : fl);
+        L.grad[i] = take(bwd(fl));
     }
     for (int i = 0; i < L.unet.nops; ++i) {
         const Op& op = L.unet.ops[i];
@@ -146,38 +154,41 @@ Layout make_layout(const paig_task* t, int B) {
     max_w = head > max_w ? head : max_w;
     sum_w += align64(head);                 // every layer keeps its own partials when the folds are batched
     max_w = sum_w > max_w ? sum_w : max_w;
+    if (inf) max_w = 0;
     L.logits = take(N * d.n * d.HW);
-    L.d_logits = take(N * d.n * d.HW);
+    L.d_logits = take(bwd(N * d.n * d.HW));
     L.masks = take(N * (d.n + 1) * d.HW);
     L.A = take(nN * L.K);
-    L.dA = take(nN * L.K);
+    L.dA = take(bwd(nN * L.K));
     L.H1 = take(nN * kHidden); L.H2 = take(nN * kHidden); L.O3 = take(nN * 2);
-    L.dH1 = take(nN * kHidden); L.dH2 = take(nN * kHidden); L.dO3 = take(nN * 2);
+    L.dH1 = take(bwd(nN * kHidden)); L.dH2 = take(bwd(nN * kHidden)); L.dO3 = take(bwd(nN * 2));
     L.enc_pos = take(N * 2 * d.n);
-    L.d_enc_pos = take(N * 2 * d.n);
+    L.d_enc_pos = take(bwd(N * 2 * d.n));
     const int vin = 2 * d.in;
     L.vin = take(nB * vin); L.v1 = take(nB * kVelHidden); L.v2 = take(nB * kVelHidden); L.vout = take(nB * 2);
-    L.dvin = take(nB * vin); L.dv1 = take(nB * kVelHidden); L.dv2 = take(nB * kVelHidden); L.dvout = take(nB * 2);
+    L.dvin = take(bwd(nB * vin)); L.dv1 = take(bwd(nB * kVelHidden)); L.dv2 = take(bwd(nB * kVelHidden)); L.dvout = take(bwd(nB * 2));
     const size_t seq = (size_t)B * (d.steps + 1) * 4 * d.n;
     L.seq = take(seq);
-    L.d_seq = take(seq);
-    L.d_state0 = take((size_t)B * 4 * d.n);
+    L.d_seq = take(bwd(seq));
+    L.d_state0 = take(bwd((size_t)B * 4 * d.n));
     const size_t CN = (size_t)d.n * d.t * d.t * 4 + 3 * d.HW;
-    L.raw = take(CN); L.consts = take(CN); L.hidden = take(3 * kHidden); L.d_consts = take(CN);
-    L.dec_partials = take(decode_partials_floats(t));
-    L.tmpl_scratch = take(templates_scratch_floats(t));
+    L.raw = take(CN); L.consts = take(CN); L.hidden = take(3 * kHidden); L.d_consts = take(bwd(CN));
+    L.dec_partials = take(bwd(decode_partials_floats(t)));
+    L.tmpl_scratch = take(bwd(templates_scratch_floats(t)));
     L.sse = take((size_t)B * (d.e + d.steps));
     L.scales = take(d.e + d.steps);
     L.losses = take(8);
-    L.dphys = take(2 * rollout_scratch_doubles(B));   // arrival counter + per-block fp64 partials of the rollout backward
+    L.dphys = take(bwd(2 * rollout_scratch_doubles(B)));   // arrival counter + per-block fp64 partials of the rollout backward
     {   // room for the split-K partials of encoder.l1 forward ([splits][nN][200]) and weight gradient ([splits][200][K])
-        const size_t fwd = (size_t)cdiv(L.K, 256) * nN * kHidden, wg = 4 * (size_t)kHidden * L.K;
+        const size_t fwd = (size_t)cdiv(L.K, 256) * nN * kHidden, wg = bwd(4 * (size_t)kHidden * L.K);
         const size_t sk = fwd > wg ? fwd : wg;
         max_w = sk > max_w ? sk : max_w;
     }
     L.partials = take(max_w);
     L.partials_floats = max_w;
-    L.tc_scratch = take((size_t)L.K * kHidden + (size_t)kHidden * nN + (size_t)L.K * nN);
+    L.partials2_floats = bwd(4 * (size_t)kHidden * L.K);      // encoder.l1 weight gradient's split-K partials: it runs on
+    L.partials2 = take(L.partials2_floats);                   // a side stream beside the UNet backward (own scratch)
+    L.tc_scratch = take(bwd((size_t)L.K * kHidden + (size_t)kHidden * nN + (size_t)L.K * nN));
     {
         size_t mx = 64;
         if (t->deep_unet)
@@ -189,9 +200,9 @@ Layout make_layout(const paig_task* t, int B) {
         L.convtc = take(mx);
     }
     L.wpack = take(unet_wpack_floats(L.unet, t));
-    L.frames = take(N * d.CHW);
-    L.x_stage = take((size_t)B * d.T * d.CHW);
-    L.x_stage2 = take((size_t)B * d.T * d.CHW);
+    L.frames = take(acts_on_chip ? 0 : N * d.CHW);
+    L.x_stage = take(bwd((size_t)B * d.T * d.CHW));
+    L.x_stage2 = take(bwd((size_t)B * d.T * d.CHW));
     L.total = off;
     return L;
 }
@@ -264,15 +275,23 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
     if (frc == 0) {
         ReduceBatch folds;                               // one launch folds every layer's per-CTA partials at the end
         size_t poff = 0;
+        // the layers' weight gradients are independent of one another: dealt over three streams, the tail wave of one
+        // launch overlaps the first wave of the next (each layer keeps its own partials region)
+        Side* sd = side_cur();
+        cudaStream_t lanes[3] = {st, sd ? sd->s1 : st, sd ? sd->s2 : st};
+        if (sd) { sd->fork1(); sd->fork2(); }
+        int lane = 0;
         for (int i = L.unet.nops - 1; i >= 0; --i) {
             const Op& op = L.unet.ops[i];
             int rc = 0;
+            cudaStream_t ls = lanes[lane % 3];
             if (op.kind == OP_HEAD) {
                 View v = view_of(L, ws, op.in, false);
                 rc = conv1x1_backward(v.p, v.bs, op.in.C, p->conv[op.layer].w, ws + L.d_logits, (long)d.n * d.HW,
                                       op.relu ? ws + L.logits : nullptr, (long)d.n * d.HW, d.n, d.H, L.N, nullptr, 0,
-                                      g->conv[op.layer].w, g->conv[op.layer].b, partials + poff, st, &folds);
+                                      g->conv[op.layer].w, g->conv[op.layer].b, partials + poff, ls, &folds);
                 poff += align64((size_t)592 * (kMaxObjs * 17));
+                ++lane;
             } else if (op.kind == OP_CONV) {
                 View o = view_of(L, ws, op.out, false), go = view_of(L, ws, op.out, true);
                 WgradArgs w;
@@ -288,10 +307,12 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
                 w.S = o.S; w.N = L.N; w.partials = partials + poff;
                 w.defer = &folds;
                 poff += align64(wgrad_partials_floats(op.in.C, op.out.C));
-                rc = conv3x3_wgrad(w, g->conv[op.layer].w, g->conv[op.layer].b, st);
+                rc = conv3x3_wgrad(w, g->conv[op.layer].w, g->conv[op.layer].b, ls);
+                ++lane;
             }
             if (rc) return rc;
         }
+        if (sd) { sd->join1(); sd->join2(); }
         return reduce_partials_batch(folds, st);
     }
     for (int i = L.unet.nops - 1; i >= 0; --i) {
@@ -618,6 +639,12 @@ static size_t enc_tail_smem(bool bwd) {
 }
 constexpr int kTailStride = kHidden * kHidden + 2 * kHidden + kHidden + 4;      // floats per CTA partial
 
+static bool l1_wgrad_on_tc(int M) {
+    static const bool tc_off = getenv("PAIG_NO_TCGEN05") != nullptr;
+    static const int tc_mask = getenv("PAIG_TC_MASK") ? atoi(getenv("PAIG_TC_MASK")) : 6;
+    return !tc_off && (tc_mask & 2) && M >= 128 && (M % 4) == 0;
+}
+
 int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride,
                     int fps, float* enc_pos_out, float* enc_masks_out, float* masked_out, float* ws, cudaStream_t st) {
     const Dims& d = L.d;
@@ -625,11 +652,15 @@ int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, c
     // The mask stage indexes frames as x + (f/fps)*seq_stride + (f%fps)*CHW; conv3x3 wants a plain batch stride,
     // so when the encoded frames are only a prefix of each sequence they are gathered once (kept for backward).
     const float* frames = x;
-    if (seq_stride != (long)fps * d.CHW) {
+    static const bool layerwise0 = getenv("PAIG_UNET_LAYERWISE") != nullptr;
+    const bool no_gather = (t->flags & PAIG_FLAG_INFERENCE) && !t->deep_unet && !layerwise0 && d.H <= 36;
+    Side* sd = side_cur();
+    const bool fused_path = !layerwise0 && !t->deep_unet;          // the fused forward reads x itself: only the
+    if (seq_stride != (long)fps * d.CHW && !no_gather) {           // backward's c1 weight gradient wants the gathered copy
         float* dst = ws + L.frames;
         const long total4 = (long)L.N * d.CHW / 4;
-        launch(gather_frames_kernel, dim3(cdiv(total4, 256)), dim3(256), 0, st, (const float4*)x, seq_stride / 4, fps,
-               d.CHW / 4, total4, (float4*)dst);
+        launch(gather_frames_kernel, dim3(cdiv(total4, 256)), dim3(256), 0, (sd && fused_path) ? sd->s1 : st, (const float4*)x,
+               seq_stride / 4, fps, d.CHW / 4, total4, (float4*)dst);
         int rc0 = check_launch("gather_frames");
         if (rc0) return rc0;
         frames = dst;
@@ -647,10 +678,17 @@ int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, c
         default: rc = masks_fwd<3>(L, t->deep_unet, ws, x, seq_stride, fps, masks, masked_out, st); break;
     }
     if (rc) return rc;
-    if (enc_masks_out)
+    if (enc_masks_out &&
         cudaMemcpyAsync(enc_masks_out, masks, (size_t)L.N * (d.n + 1) * d.HW * sizeof(float), cudaMemcpyDeviceToDevice,
-                        st);
+                        st) != cudaSuccess)
+        return check_launch("copy enc_masks");
     const int M = d.n * L.N;
+    if (sd && l1_wgrad_on_tc(M)) {
+        // the backward's encoder.l1 weight gradient wants A^T: transpose it now, beside the MLP / rollout / decoder chain
+        sd->fork1();
+        float* At = ws + L.tc_scratch + (size_t)L.K * kHidden + (size_t)kHidden * M;
+        if ((rc = transpose(ws + L.A, At, M, L.K, sd->s1))) return rc;
+    }
     {   // encoder.l1: tcgen05 3xTF32 when the shape qualifies (gemm_tc.cu), else the CUDA-core GEMM
         // Which encoder.l1 GEMMs run on tcgen05 (1 forward | 2 weight gradient | 4 data gradient).  Default 6: the two
         // backward GEMMs.  The forward product stays on the fp32 FMA pipe: the tensor core accumulates with
@@ -723,29 +761,40 @@ int encoder_backward(const paig_task* t, const paig_params* p, const paig_params
     if ((rc = linear_dgrad(ws + L.dH2, p->enc_l2.w, ws + L.dH1, M, kHidden, kHidden, EPI_MASK_RELU, ws + L.H1, st)))
         return rc;
     }
-    // l1
+    // l1: the weight gradient (transposes + tcgen05 GEMM + fold + bias column sums, ~110 us) does not feed the data
+    // gradient: in the fused step it runs on a side stream beside the data-gradient GEMM and the UNet backward
     {
+        Side* sd = side_cur();
+        cudaStream_t wst = sd ? sd->s1 : st;
         float* Wt = ws + L.tc_scratch;                       // [K][200]
         float* dHt = Wt + (size_t)L.K * kHidden;             // [200][M]
-        float* At = dHt + (size_t)kHidden * M;               // [K][M]
+        float* At = dHt + (size_t)kHidden * M;               // [K][M]   (already filled by encoder_forward when sd)
+        float* wpart = sd ? ws + L.partials2 : ws + L.partials;
+        const size_t wpart_floats = sd ? L.partials2_floats : L.partials_floats;
         int sp = -1;
         static const bool tc_off = getenv("PAIG_NO_TCGEN05") != nullptr;
         static const int tc_mask = getenv("PAIG_TC_MASK") ? atoi(getenv("PAIG_TC_MASK")) : 6;
-        if (!tc_off && (tc_mask & 2) && M >= 128 && (M % 4) == 0) {
+        if (sd) sd->fork1();
+        if (l1_wgrad_on_tc(M)) {
             // dW1[200,K] = dH1^T[200,M] . A^T[K,M]^T : both operands transposed once so that M is the contiguous K axis
-            if ((rc = transpose(ws + L.dH1, dHt, M, kHidden, st))) return rc;
-            if ((rc = transpose(ws + L.A, At, M, L.K, st))) return rc;
-            sp = gemm_tc_partials(dHt, At, kHidden, L.K, M, false, ws + L.partials, L.partials_floats, "tc_l1_wgrad", st);
+            if ((rc = transpose(ws + L.dH1, dHt, M, kHidden, wst))) return rc;
+            if (!sd && (rc = transpose(ws + L.A, At, M, L.K, wst))) return rc;
+            sp = gemm_tc_partials(dHt, At, kHidden, L.K, M, false, wpart, wpart_floats, "tc_l1_wgrad", wst);
             if (sp == 0) return 2;
         }
         if (sp > 0) {
             GemmArgs gg;
-            gg.C = g->enc_l1.w; gg.ldc = L.K; gg.M = kHidden; gg.N = L.K; gg.splitk_ws = ws + L.partials;
-            if ((rc = gemm_fold_partials(gg, sp, st))) return rc;
-            if (g->enc_l1.b && (rc = colsum(ws + L.dH1, M, kHidden, kHidden, g->enc_l1.b, st))) return rc;
-        } else if ((rc = linear_wgrad(ws + L.dH1, ws + L.A, g->enc_l1.w, g->enc_l1.b, M, L.K, kHidden, st, ws + L.partials,
-                                      L.partials_floats, "sgemm_l1_wgrad")))
+            gg.C = g->enc_l1.w; gg.ldc = L.K; gg.M = kHidden; gg.N = L.K; gg.splitk_ws = wpart;
+            if ((rc = gemm_fold_partials(gg, sp, wst))) return rc;
+            if (g->enc_l1.b && (rc = colsum(ws + L.dH1, M, kHidden, kHidden, g->enc_l1.b, wst))) return rc;
+        } else if ((rc = linear_wgrad(ws + L.dH1, ws + L.A, g->enc_l1.w, g->enc_l1.b, M, L.K, kHidden, wst, wpart,
+                                      wpart_floats, "sgemm_l1_wgrad")))
             return rc;
+#ifndef PAIG_EMU
+        // every gradient except the UNet conv layers' is final here (the VariableFromNetwork ones were enqueued on the
+        // same side stream earlier): the data-parallel caller starts their all-reduce behind this event
+        if (g_early_event) cudaEventRecord((cudaEvent_t)g_early_event, wst);
+#endif
         // dA[M,K] = dH1[M,200] . (W1^T)[K,200]^T : one K split, written in place
         sp = -1;
         if (!tc_off && (tc_mask & 4) && M >= 128) {

@@ -6,6 +6,22 @@ namespace paig {
 
 bool valid_task(const paig_task* t);
 
+// side.cu -- the fused step's side streams (nullptr: run everything in line on the caller's stream)
+struct Side {
+    cudaStream_t main = nullptr, s1 = nullptr, s2 = nullptr;
+    void* set = nullptr;
+    void after(cudaStream_t waiter, cudaStream_t signaler);     // waiter waits for all work enqueued on signaler so far
+    void fork1() { after(s1, main); }
+    void fork2() { after(s2, main); }
+    void join1() { after(main, s1); }
+    void join2() { after(main, s2); }
+};
+Side* side_begin(cudaStream_t main);
+void side_end();
+Side* side_cur();
+// an event the caller wants recorded once every gradient EXCEPT the UNet conv layers' is final (data-parallel overlap)
+extern thread_local void* g_early_event;
+
 // rollout.cu
 // a_frozen: 0, or the gravity cell's constructor-time A (paig_task.gravity_A)
 int rollout_forward(int cell, int n, int B, int steps, const float* dt, const double* p0, const double* p1,
@@ -24,6 +40,9 @@ struct DecSeg {
     const float* target = nullptr;   // frame the output is compared with: target + q*tgt_seq_stride + r*3*H*H
     long tgt_seq_stride = 0;
     const float* scale = nullptr;    // [fps] loss weight s_r: in-kernel upstream gradient is 2*s_r*(out - target)
+    int use_scale = 0;               // ... or by value: s_r = r < scale_split ? scale_lo : scale_hi
+    int scale_split = 0;
+    float scale_lo = 0.f, scale_hi = 0.f;
     const float* dframes = nullptr;  // [nframes,3,H,H] upstream gradient from memory (overrides scale)
     float* frames = nullptr;         // [nframes,3,H,H] decoded output (nullable)
     float* sse = nullptr;            // [nframes] sum of squared error vs target (nullable)

@@ -47,6 +47,7 @@ struct Layout {
     size_t sse, scales, losses, dphys;
     size_t partials;             // conv wgrad / head partial sums; split-K partials of the MLP GEMMs
     size_t partials_floats;
+    size_t partials2, partials2_floats;   // side-stream scratch of the encoder.l1 weight gradient
     size_t tc_scratch;           // transposed operands of the tcgen05 encoder.l1 GEMMs: W1^T | dH1^T | A^T
     size_t convtc;               // packed weights of the layer in flight on the tcgen05 conv path (deep UNet)
     size_t wpack;                // UNet weights re-packed [ci][tap][co]|bias for the fused forward kernel

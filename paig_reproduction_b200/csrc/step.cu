@@ -12,13 +12,6 @@
 
 namespace paig {
 
-// scales[0:e) = alpha/(Bg*e) recons weights ; scales[e:e+steps) = 1/(Bg*pr) for s < pr, else 0
-__global__ void loss_scales_kernel(float* __restrict__ scales, int e, int steps, int pr, float alpha, float Bg) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < e) scales[i] = alpha > 0.f ? alpha / (Bg * (float)e) : 0.f;
-    else if (i < e + steps) scales[i] = (i - e) < pr ? 1.f / (Bg * (float)pr) : 0.f;
-}
-
 // losses = [train, pred, extrap, recons]  (physics_models.py:122-141; means over the GLOBAL batch, so
 // data-parallel shards sum to the job's loss).  One block, fixed order.
 __global__ void __launch_bounds__(256) loss_finalize_kernel(const float* __restrict__ sse, int B, int e, int steps, int pr,
@@ -77,17 +70,21 @@ static int forward_common(const paig_task* t, const paig_params* p, const Layout
                           const paig_outputs* out, float* ws, cudaStream_t st) {
     const Dims& d = L.d;
     int rc;
+    Side* sd = side_cur();                            // fused step: the VariableFromNetwork branch runs beside the encoder
+    if (sd) sd->fork1();
     if ((rc = templates_forward(t, p, out && out->templates ? out->templates : ws + L.raw, ws + L.consts,
-                                ws + L.hidden, st)))
+                                ws + L.hidden, sd ? sd->s1 : st)))
         return rc;
     if ((rc = encoder_forward(t, p, L, x, (long)d.T * d.CHW, d.e, out ? out->enc_pos : nullptr,
                               out ? out->enc_masks : nullptr, out ? out->masked_objs : nullptr, ws, st)))
         return rc;
     if ((rc = velocity_forward(t, p, L, ws + L.enc_pos, ws, st))) return rc;
     if ((rc = rollout_forward(t->cell, d.n, L.B, d.steps, p->dt, p->phys0, p->phys1, t->gravity_A, ws + L.seq, st))) return rc;
-    if (out && out->pos_vel_seq)
+    if (out && out->pos_vel_seq &&
         cudaMemcpyAsync(out->pos_vel_seq, ws + L.seq, (size_t)L.B * (d.steps + 1) * 4 * d.n * sizeof(float),
-                        cudaMemcpyDeviceToDevice, st);
+                        cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return check_launch("copy pos_vel_seq");
+    if (sd) sd->join1();                              // decoder constants (and the side work of the encoder) are ready
     return 0;
 }
 
@@ -97,7 +94,9 @@ static int finalize_losses(const paig_task* t, const Layout& L, float* ws, float
            t->alpha, batch_global(t, L.B), ws + L.losses);
     int rc = check_launch("loss_finalize");
     if (rc) return rc;
-    if (losses_out) cudaMemcpyAsync(losses_out, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (losses_out &&
+        cudaMemcpyAsync(losses_out, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+        return check_launch("copy losses");
     return 0;
 }
 
@@ -115,8 +114,10 @@ int step_forward(const paig_task* t, const paig_params* p, const float* x, int B
 }
 
 // Everything after the decoder's backward: d_seq / d_enc_pos / d_consts are complete in the workspace.
+thread_local void* g_early_event = nullptr;
+
 static int backward_tail(const paig_task* t, const paig_params* p, const paig_params* g, const Layout& L,
-                         const float* x, float* ws, cudaStream_t st) {
+                         const float* x, float* ws, cudaStream_t st, bool templates_done = false) {
     const Dims& d = L.d;
     int rc;
     // physics-constant gradients go straight to the caller's fp64 slots (spring: k, equil; gravity: g; bouncing: none)
@@ -129,6 +130,7 @@ static int backward_tail(const paig_task* t, const paig_params* p, const paig_pa
         return rc;
     if ((rc = velocity_backward(t, p, g, L, ws + L.d_state0, ws + L.d_enc_pos, ws, st))) return rc;
     if ((rc = encoder_backward(t, p, g, L, x, (long)d.T * d.CHW, d.e, ws + L.d_enc_pos, ws, st))) return rc;
+    if (templates_done) return 0;
     return templates_backward(t, p, g, ws + L.consts, ws + L.hidden, ws + L.d_consts, ws + L.tmpl_scratch, st);
 }
 
@@ -142,9 +144,16 @@ static void route_dloc(const Layout& L, float* ws, DecSeg* A, DecSeg* R) {
     R->dloc_seq_stride = R->loc_seq_stride;
 }
 
+static bool refuse_inference(const paig_task* t, const char* what) {
+    if (!(t->flags & PAIG_FLAG_INFERENCE)) return false;
+    set_error("%s: the task carries PAIG_FLAG_INFERENCE (its workspace holds nothing for a backward pass)", what);
+    return true;
+}
+
 int step_backward(const paig_task* t, const paig_params* p, const paig_params* g, const float* x, int B,
                   const float* d_output_seq, const float* d_recons_out, const float* d_enc_pos,
                   const float* d_pos_vel_seq, float* ws, cudaStream_t st) {
+    if (refuse_inference(t, "step_backward")) return 1;
     const Layout L = make_layout(t, B);
     const Dims& d = L.d;
     const size_t seq_fl = (size_t)B * (d.steps + 1) * 4 * d.n, ep_fl = (size_t)L.N * 2 * d.n;
@@ -179,26 +188,50 @@ int step_backward(const paig_task* t, const paig_params* p, const paig_params* g
     return backward_tail(t, p, g, L, x, ws, st);
 }
 
+namespace {
+struct SideScope {                                   // side streams live for exactly one fused step
+    Side* sd;
+    explicit SideScope(cudaStream_t st) : sd(side_begin(st)) {}
+    ~SideScope() { if (sd) side_end(); }
+};
+}  // namespace
+
 int step_fused(const paig_task* t, const paig_params* p, const paig_params* g, const float* x, int B,
                const paig_outputs* out, float* ws, cudaStream_t st) {
+    if (refuse_inference(t, "step_fused")) return 1;
     const Layout L = make_layout(t, B);
     const Dims& d = L.d;
+    SideScope scope(st);
+    Side* sd = scope.sd;
     int rc = forward_common(t, p, L, x, out, ws, st);
     if (rc) return rc;
-    launch(loss_scales_kernel, dim3(1), dim3(256), 0, st, ws + L.scales, d.e, d.steps, d.pr, t->alpha,
-           batch_global(t, B));
-    if ((rc = check_launch("loss_scales"))) return rc;
-    cudaMemsetAsync(ws + L.d_seq, 0, (size_t)B * (d.steps + 1) * 4 * d.n * sizeof(float), st);
+    if (cudaMemsetAsync(ws + L.d_seq, 0, (size_t)B * (d.steps + 1) * 4 * d.n * sizeof(float), st) != cudaSuccess)
+        return check_launch("memset d_seq");
     DecSeg A, R;
     segments(t, L, ws, x, &A, &R);
     route_dloc(L, ws, &A, &R);
-    A.scale = ws + L.scales;
-    R.scale = ws + L.scales + d.e;
+    // loss weights of the in-kernel upstream gradient 2 s_r (out - target): alpha/(Bg e) on every reconstruction
+    // frame; 1/(Bg pr) on the first pr rollout frames, 0 on the extrapolation frames (physics_models.py:122-139)
+    const float Bg = batch_global(t, B);
+    A.scale_lo = A.scale_hi = t->alpha > 0.f ? t->alpha / (Bg * (float)d.e) : 0.f;
+    A.scale_split = d.e;
+    R.scale_lo = 1.f / (Bg * (float)d.pr);
+    R.scale_hi = 0.f;
+    R.scale_split = d.pr;
+    A.use_scale = R.use_scale = 1;
     A.frames = out ? out->recons_out : nullptr;       // normally NULL: the fused step never writes frames
     R.frames = out ? out->output_seq : nullptr;
     if ((rc = decode_run(t, ws + L.consts, A, R, true, ws + L.dec_partials, ws + L.d_consts, 0, st))) return rc;
-    if ((rc = finalize_losses(t, L, ws, out ? out->losses : nullptr, st))) return rc;
-    return backward_tail(t, p, g, L, x, ws, st);
+    // the loss scalars and the VariableFromNetwork backward only need the decoder's results: beside the main chain
+    cudaStream_t ts = sd ? sd->s1 : st;
+    if (sd) sd->fork1();
+    if ((rc = finalize_losses(t, L, ws, out ? out->losses : nullptr, ts))) return rc;
+    if (sd && (rc = templates_backward(t, p, g, ws + L.consts, ws + L.hidden, ws + L.d_consts, ws + L.tmpl_scratch, ts)))
+        return rc;
+    if ((rc = backward_tail(t, p, g, L, x, ws, st, sd != nullptr))) return rc;
+    if (sd) { sd->join1(); sd->join2(); }
+    g_early_event = nullptr;                          // armed for one step (paig_set_early_grad_event)
+    return 0;
 }
 
 }  // namespace paig
@@ -229,6 +262,8 @@ int paig_step_backward(const paig_task* t, const paig_params* p, const paig_para
                          (cudaStream_t)stream);
 }
 
+void paig_set_early_grad_event(void* cuda_event) { g_early_event = cuda_event; }
+
 int paig_step_fused(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x, int B,
                     const paig_outputs* out, void* workspace, void* stream) {
     if (!valid_task(t)) return 1;
@@ -237,7 +272,7 @@ int paig_step_fused(const paig_task* t, const paig_params* p, const paig_params*
 
 int paig_step_fused_host(const paig_task* t, const paig_params* p, const paig_params* grads, const float* x_host, int B,
                          float* losses_host, void* workspace, void* stream) {
-    if (!valid_task(t)) return 1;
+    if (!valid_task(t) || refuse_inference(t, "step_fused_host")) return 1;
     const Layout L = make_layout(t, B);
     float* ws = (float*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
@@ -254,7 +289,7 @@ static cudaEvent_t g_stage_ev[2] = {nullptr, nullptr};
 #endif
 
 int paig_stage_input_host(const paig_task* t, const float* x_host, int B, int slot, void* workspace, void* copy_stream) {
-    if (!valid_task(t)) return 1;
+    if (!valid_task(t) || refuse_inference(t, "stage_input_host")) return 1;
     if (slot != 0 && slot != 1) { set_error("stage_input_host: slot must be 0 or 1"); return 1; }
     const Layout L = make_layout(t, B);
     float* ws = (float*)workspace;

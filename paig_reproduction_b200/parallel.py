@@ -1,10 +1,17 @@
 """Data-parallel training step: sequences are independent, so the batch is sharded by sequence across ranks
-(one process per GPU) and the only exchange is one sum all-reduce of the flat gradient buffer (+ the loss
-scalars riding at its end) and a 16-byte fp64 all-reduce for the physics constants.  SURVEY section 8(e).
+(one process per GPU) and the only exchange is the sum all-reduce of the gradients.  SURVEY section 8(e).
+
+The flat gradient buffer is ordered [everything but the UNet conv layers | UNet conv layers | 4 loss scalars]
+(``PhysicsNet.flat_order``).  The first part -- VariableFromNetworks, encoder MLP, velocity MLP: 98 % of the bytes -- is
+final before the UNet backward starts; the library records an event at that point (``paig_set_early_grad_event``) and
+the all-reduce of that prefix, and of the 16-byte fp64 physics gradients, is launched on a side stream behind the event,
+underneath the UNet backward and weight-gradient kernels.  Only the all-reduce of the 34 k conv gradients + losses
+(138 KB, latency bound) remains after the step.
 
 The reference has no distributed code at all (single device, runners/torch_run_physics.py:78)."""
 from __future__ import annotations
 
+import os
 from typing import Tuple
 
 import torch
@@ -19,9 +26,13 @@ def shard_bounds(batch: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def _active(group) -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+
 def allreduce_step(flat_grad: torch.Tensor, phys_grad: torch.Tensor, group=None) -> None:
-    """Sum the step's gradients (and the 4 loss scalars at the tail of flat_grad) over the job."""
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+    """Sum the step's gradients (and the 4 loss scalars at the tail of flat_grad) over the job, in line."""
+    if not _active(group):
         return
     dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
     if phys_grad is not None and phys_grad.numel():
@@ -30,15 +41,53 @@ def allreduce_step(flat_grad: torch.Tensor, phys_grad: torch.Tensor, group=None)
 
 class DataParallelStep:
     """Wraps a PhysicsNet: `step(x_local)` runs the fused LIVE step on this rank's shard with the job-wide loss
-    normalisation, then all-reduces.  Every rank ends with the gradient of the global-batch loss."""
+    normalisation and all-reduces.  Every rank ends with the gradient of the global-batch loss.  With `overlap` (default
+    on CUDA) the bulk of the all-reduce runs underneath the UNet backward (module docstring)."""
 
-    def __init__(self, net, global_batch: int, group=None):
+    def __init__(self, net, global_batch: int, group=None, overlap: bool | None = None):
         self.net = net
         self.group = group
         self.global_batch = int(global_batch)
         net.batch_global = self.global_batch
+        if overlap is None:
+            overlap = os.environ.get("PAIG_DP_OVERLAP", "1") != "0"
+        self.overlap = bool(overlap) and net.device.type == "cuda"
+        self._side = self._event = None
+
+    def _setup(self):
+        self._side = torch.cuda.Stream(self.net.device)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(self.net.device))      # materialise the cudaEvent_t behind it
+
+    def arm(self) -> bool:
+        """Before enqueuing a fused step: arm the early-gradient event.  False: the all-reduce will run in line."""
+        if not (self.overlap and _active(self.group)):
+            return False
+        from . import _lib
+        if self._side is None:
+            self._setup()
+        self.net.flat_gradients()
+        _lib.load().paig_set_early_grad_event(self._event.cuda_event)
+        return True
+
+    def reduce(self, armed: bool) -> None:
+        """After the step was enqueued: launch the all-reduces (the early part behind the event on the side stream)."""
+        net = self.net
+        flat = net.flat_gradients()
+        if not armed:
+            allreduce_step(flat, net._phys_grad, self.group)
+            return
+        main = torch.cuda.current_stream(net.device)
+        self._side.wait_event(self._event)
+        with torch.cuda.stream(self._side):
+            dist.all_reduce(flat[:net.flat_early], op=dist.ReduceOp.SUM, group=self.group)
+            if net._phys_grad.numel():
+                dist.all_reduce(net._phys_grad, op=dist.ReduceOp.SUM, group=self.group)
+        dist.all_reduce(flat[net.flat_early:], op=dist.ReduceOp.SUM, group=self.group)    # UNet conv gradients + losses
+        main.wait_stream(self._side)
 
     def step(self, x_local: torch.Tensor) -> torch.Tensor:
-        losses = self.net.train_step(x_local)
-        allreduce_step(self.net.flat_gradients(), self.net._phys_grad, self.group)
+        armed = self.arm()
+        losses = self.net.train_step(x_local)             # enqueues the whole step; the library records the event mid-way
+        self.reduce(armed)
         return losses

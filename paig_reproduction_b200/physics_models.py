@@ -219,11 +219,11 @@ class PhysicsNet(BaseNetTorch):
         self.optimizer = None
 
     # ------------------------------------------------------------------ C-ABI plumbing
-    def _task(self, T: int) -> _abi.Task:
+    def _task(self, T: int, inference: bool = False) -> _abi.Task:
         frozen = self._gravity_A0 if (self.freeze_gravity_A and self.cell_kind == "gravity") else 0.0
         return _abi.Task(_abi.CELL_IDS[self.cell_kind], self.n_objs, self.H, T, self.input_steps, self.pred_steps,
                          int(self.alt_vel), int(self.deep), float(self.autoencoder_loss), int(self.batch_global),
-                         float(frozen), 0)
+                         float(frozen), _abi.FLAG_INFERENCE if inference else 0)
 
     def live_parameter_names(self, with_rollout: bool = True) -> List[str]:
         """state_dict keys that receive a gradient in a LIVE step, in state_dict order."""
@@ -251,13 +251,13 @@ class PhysicsNet(BaseNetTorch):
     def _params_now(self) -> Dict[str, torch.Tensor]:
         return {k: v.data for k, v in self.named_parameters()}
 
-    def _workspace(self, T: int, B: int, fresh: bool) -> torch.Tensor:
+    def _workspace(self, T: int, B: int, fresh: bool, inference: bool = False) -> torch.Tensor:
         lib = _lib.load()
-        tk = self._task(T)
+        tk = self._task(T, inference)
         n = lib.paig_workspace_bytes(ctypes.byref(tk), B)
         if n == 0:
             raise _lib.PaigError(lib.paig_last_error().decode())
-        key = (T, B)
+        key = (T, B, inference)
         if fresh:
             pool = self._ws_pools.setdefault(key, _Pool())
             ws = pool.pop() if pool else torch.empty(n // 4 + 64, dtype=torch.float32, device=self.device)
@@ -281,7 +281,8 @@ class PhysicsNet(BaseNetTorch):
         B, T = x.shape[0], x.shape[1]
         n, H, e, steps = self.n_objs, self.H, self.input_steps + self.pred_steps, T - self.input_steps
         dev = self.device
-        lease = self._workspace(T, B, fresh=True) if need_backward else _Lease(None, self._workspace(T, B, fresh=False))
+        # under no_grad (eval_performance, base.py:179) nothing is kept for a backward pass: inference plan, small workspace
+        lease = self._workspace(T, B, fresh=True) if need_backward else _Lease(None, self._workspace(T, B, False, inference=True))
         ws = lease.ws
         out = dict(output_seq=torch.empty(B, steps, 3, H, H, device=dev), recons_out=torch.empty(B, e, 3, H, H, device=dev),
                    enc_pos=torch.empty(B, e, 2 * n, device=dev), pos_vel_seq=torch.empty(B, steps + 1, 4 * n, device=dev),
@@ -290,7 +291,7 @@ class PhysicsNet(BaseNetTorch):
                    templates=torch.empty(n * (H // 2) ** 2 * 4 + 3 * H * H, device=dev), losses=torch.empty(4, device=dev))
         O = _abi.Outputs(*[out[k].data_ptr() for k in ("output_seq", "recons_out", "enc_pos", "pos_vel_seq", "enc_masks",
                                                        "masked_objs", "templates", "losses")])
-        tk = self._task(T)
+        tk = self._task(T, inference=not need_backward)
         params = self._params_now()
         P = self._param_table(params)
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -450,21 +451,35 @@ class PhysicsNet(BaseNetTorch):
         return {"input": batch_x}, (batch_x, None)
 
     # ------------------------------------------------------------------ fused LIVE step (the fast path)
+    def flat_order(self) -> List[str]:
+        """fp32 live parameters in flat-buffer order: everything EXCEPT the UNet conv layers first (their gradients are
+        final before the UNet backward starts, so a data-parallel job can all-reduce that prefix underneath it), the UNet
+        conv layers last."""
+        params = dict(self.named_parameters())
+        names = [k for k in self.live_parameter_names() if params[k].dtype == torch.float32]
+        conv = "encoder." + self._unet + "."
+        return [k for k in names if not k.startswith(conv)] + [k for k in names if k.startswith(conv)]
+
     def flat_gradients(self) -> torch.Tensor:
         """One contiguous fp32 buffer holding the gradient of every live fp32 parameter (+ the 4 loss scalars at the
-        end), so a data-parallel job needs a single all-reduce.  ``p.grad`` of each parameter is a view into it."""
+        end), so a data-parallel job needs one all-reduce (or two: ``flat_early`` floats that are final early, then the
+        rest).  ``p.grad`` of each parameter is a view into it."""
         if self._flat_grad is None:
             params = dict(self.named_parameters())
-            names = [k for k in self.live_parameter_names() if params[k].dtype == torch.float32]
+            names = self.flat_order()
+            conv = "encoder." + self._unet + "."
             total = sum(params[k].numel() for k in names)
             total_al = (total + 3) // 4 * 4
             flat = torch.zeros(total_al + 4, dtype=torch.float32, device=self.device)
             off = 0
             self._grad_views = {}
+            self.flat_early = 0
             for k in names:
                 n = params[k].numel()
                 self._grad_views[k] = flat[off:off + n].view_as(params[k])
                 off += n
+                if not k.startswith(conv):
+                    self.flat_early = off
             self._loss_view = flat[total_al:total_al + 4]
             self._phys_grad = torch.zeros(2, dtype=torch.float64, device=self.device)
             i = 0

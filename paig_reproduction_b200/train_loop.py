@@ -34,7 +34,7 @@ class FusedOptimizer:
         self.flat_grad = net.flat_gradients()
         params = dict(net.named_parameters())
         names = [k for k in net.live_parameter_names()]
-        self.f32 = [k for k in names if params[k].dtype == torch.float32]
+        self.f32 = net.flat_order()                                     # same order as the flat gradient buffer
         self.f64 = [k for k in names if params[k].dtype == torch.float64]
         n = sum(params[k].numel() for k in self.f32)
         dev = self.flat_grad.device

@@ -97,3 +97,21 @@ def test_constructor_errors_match_reference():
         PhysicsNet(*(a[:3] + ["lstm_cell"] + a[4:]), device="cpu")
     with pytest.raises(AssertionError):
         PhysicsNet(*(["no_such_task"] + a[1:]), device="cpu")
+
+
+@pytest.mark.parametrize("task", list(RUNNER_ARGS))
+def test_flat_gradient_order_puts_the_unet_last(task):
+    """parallel.py all-reduces the prefix of the flat gradient buffer underneath the UNet backward: that prefix must
+    hold every live fp32 parameter except the UNet conv layers, and be the bulk of the bytes."""
+    from paig_reproduction_b200.physics_models import PhysicsNet
+    net = PhysicsNet(*RUNNER_ARGS[task], device="cpu")
+    order = net.flat_order()
+    params = dict(net.named_parameters())
+    live = [k for k in net.live_parameter_names() if params[k].dtype == torch.float32]
+    assert sorted(order) == sorted(live) and len(set(order)) == len(order)
+    conv = "encoder." + ("unet." if task == "mnist_spring_color" else "shallow_unet.")
+    first_conv = min(i for i, k in enumerate(order) if k.startswith(conv))
+    assert all(k.startswith(conv) for k in order[first_conv:]) and not any(k.startswith(conv) for k in order[:first_conv])
+    early = sum(params[k].numel() for k in order[:first_conv])
+    total = sum(params[k].numel() for k in order)
+    assert early / total > (0.9 if task != "mnist_spring_color" else 0.85)
