@@ -4,9 +4,16 @@
 The flat gradient buffer is ordered [everything but the UNet conv layers | UNet conv layers | 4 loss scalars]
 (``PhysicsNet.flat_order``).  The first part -- VariableFromNetworks, encoder MLP, velocity MLP: 98 % of the bytes -- is
 final before the UNet backward starts; the library records an event at that point (``paig_set_early_grad_event``) and
-the all-reduce of that prefix, and of the 16-byte fp64 physics gradients, is launched on a side stream behind the event,
-underneath the UNet backward and weight-gradient kernels.  Only the all-reduce of the 34 k conv gradients + losses
-(138 KB, latency bound) remains after the step.
+with ``overlap=True`` the all-reduce of that prefix, and of the 16-byte fp64 physics gradients, is launched on a side
+stream behind the event, underneath the UNet backward and weight-gradient kernels, leaving only the 34 k conv gradients
++ losses (138 KB) for after the step.
+
+MEASURED (2 x B200, profiles/r2i_bench_n2*.json): the overlapped form is SLOWER -- 3.31 ms per step against 2.75 ms
+with one all-reduce after the step (2.71 ms on one GPU).  The UNet backward is a persistent kernel that wants every SM
+(one 512-thread CTA with 214 KB of shared memory each); the NCCL kernel's CTAs take some of them first, the frames those
+SMs own start late, and both ranks then wait on each other's late kernels.  So the default is the plain all-reduce
+after the step (98.3 % weak-scaling efficiency at N = 2); the overlap path stays selectable (PAIG_DP_OVERLAP=1) for
+configurations whose backward does not fill the GPU.
 
 The reference has no distributed code at all (single device, runners/torch_run_physics.py:78)."""
 from __future__ import annotations
@@ -41,8 +48,8 @@ def allreduce_step(flat_grad: torch.Tensor, phys_grad: torch.Tensor, group=None)
 
 class DataParallelStep:
     """Wraps a PhysicsNet: `step(x_local)` runs the fused LIVE step on this rank's shard with the job-wide loss
-    normalisation and all-reduces.  Every rank ends with the gradient of the global-batch loss.  With `overlap` (default
-    on CUDA) the bulk of the all-reduce runs underneath the UNet backward (module docstring)."""
+    normalisation and all-reduces.  Every rank ends with the gradient of the global-batch loss.  With `overlap` the bulk
+    of the all-reduce runs underneath the UNet backward (off by default: measured slower, module docstring)."""
 
     def __init__(self, net, global_batch: int, group=None, overlap: bool | None = None):
         self.net = net
@@ -50,7 +57,7 @@ class DataParallelStep:
         self.global_batch = int(global_batch)
         net.batch_global = self.global_batch
         if overlap is None:
-            overlap = os.environ.get("PAIG_DP_OVERLAP", "1") != "0"
+            overlap = os.environ.get("PAIG_DP_OVERLAP", "0") == "1"
         self.overlap = bool(overlap) and net.device.type == "cuda"
         self._side = self._event = None
 
