@@ -229,7 +229,9 @@ long paig_launch_count(void);
 void paig_profile_begin(void);
 int paig_profile_end(char* buf, size_t cap);
 
-/* Test hook: C[M,N] = A[M,K] . B[N,K]^T on the tcgen05 3xTF32 path (csrc/gemm_tc.cu); scratch holds the split-K partials. */
+/* Test hook: C[M,N] = A[M,K] . B[N,K]^T on the tcgen05 3xTF32 path (csrc/gemm_tc.cu); scratch holds the split-K partials.
+ * fixed_split: 0 = split chosen for occupancy, 1 = batch-invariant split by K only, 2 = the drained kernel (short TMEM
+ * accumulation chains + truncation compensation) that encoder.l1's forward product uses. */
 int paig_debug_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int fixed_split, float* scratch,
                        long scratch_floats, void* stream);
 

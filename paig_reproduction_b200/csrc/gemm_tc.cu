@@ -208,6 +208,156 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_kernel(const __grid
     }
 }
 
+// The same product for operands that feed a long ReLU / tanh chain (encoder.l1 FORWARD): the tensor core truncates its
+// fp32 accumulator after every MMA, and 144 accumulations in one TMEM accumulator shrink every pre-activation by ~2e-6,
+// which the position head amplifies past the gradient bar.  Here the hi.hi products of ONE stage
+// (4 accumulations) go to a double-buffered accumulator that the converter warps drain after every stage into register
+// sums with round-to-nearest FMAs (with the expected truncation loss of a 4-chain added back in the same FMA, see
+// csrc/conv_tc.cu), and the small hi.lo + lo.hi corrections keep their own accumulator.  BN <= 112 (3 x BN TMEM columns,
+// BN register sums per thread); the caller tiles N.
+template <int BN>
+__global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_drained_kernel(const __grid_constant__ TcArgs a) {
+    extern __shared__ __align__(1024) unsigned char tc_raw[];
+    __shared__ unsigned long long full[kTcStages], conv[kTcStages], empty[kTcStages], accfull[2], accfree[2];
+    __shared__ unsigned tmem_slot;
+    unsigned char* base = tc_raw + ((1024u - (smem_u32(tc_raw) & 1023u)) & 1023u);
+    constexpr unsigned a_bytes = kTcBM * 128u, b_bytes = (unsigned)BN * 128u;
+    constexpr unsigned stage_bytes = 2 * a_bytes + 2 * b_bytes;          // A_hi | A_lo | B_hi | B_lo
+    constexpr unsigned kCols = 3 * BN <= 256 ? 256u : 512u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * kTcBM, n0 = blockIdx.x * BN;
+    const int nkb = (a.K + kTcBK - 1) / kTcBK;
+    const int kb0 = blockIdx.z * a.kb_per;
+    const int count = min(a.kb_per, nkb - kb0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&accfull[b], 1); mbar_init(&accfree[b], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(kCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < count; ++i) {
+                const int s = i % kTcStages;
+                mbar_wait(&empty[s], (((unsigned)(i / kTcStages)) & 1u) ^ 1u);
+                unsigned char* st = base + (size_t)s * stage_bytes;
+                const unsigned bar = smem_u32(&full[s]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(a_bytes + b_bytes) : "memory");
+                const int k = (kb0 + i) * kTcBK;
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(smem_u32(st)), "l"(reinterpret_cast<uint64_t>(&a.tmA)), "r"(k), "r"(m0), "r"(bar) : "memory");
+                asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                             ::"r"(smem_u32(st + 2 * a_bytes)), "l"(reinterpret_cast<uint64_t>(&a.tmB)), "r"(k), "r"(n0), "r"(bar) : "memory");
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(BN >> 3) << 17) | ((unsigned)(kTcBM >> 4) << 24);
+            for (int i = 0; i < count; ++i) {
+                const int s = i % kTcStages;
+                const unsigned b = i & 1u, use = (unsigned)i >> 1;
+                mbar_wait(&conv[s], ((unsigned)(i / kTcStages)) & 1u);
+                if (use > 0) mbar_wait(&accfree[b], (use - 1) & 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const unsigned sa = smem_u32(base + (size_t)s * stage_bytes);
+                const unsigned sa_lo = sa + a_bytes, sb = sa + 2 * a_bytes, sb_lo = sb + b_bytes;
+                const unsigned d_main = tmem + b * BN, d_corr = tmem + 2 * BN;
+#pragma unroll
+                for (int k = 0; k < kTcBK / 8; ++k) {
+                    const uint64_t ah = umma_desc(sa + 32u * k), al = umma_desc(sa_lo + 32u * k);
+                    const uint64_t bh = umma_desc(sb + 32u * k), bl = umma_desc(sb_lo + 32u * k);
+                    umma_tf32(d_main, ah, bh, idesc, k > 0 ? 1u : 0u);
+                    umma_tf32(d_corr, ah, bl, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_tf32(d_corr, al, bh, idesc, 1u);
+                }
+                umma_commit(&empty[s]);
+                umma_commit(&accfull[b]);
+            }
+        }
+    } else {
+        const int t = threadIdx.x - 64;                                  // 0..127
+        const int q = warp & 3;
+        const unsigned lane_base = tmem + ((unsigned)(q * 32) << 16);
+        float sum[BN];
+#pragma unroll
+        for (int c = 0; c < BN; ++c) sum[c] = 0.f;
+        auto drain = [&](int i) {
+            const unsigned b = (unsigned)i & 1u, use = (unsigned)i >> 1;
+            mbar_wait(&accfull[b], use & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < BN; c += 16) {
+                unsigned v[16];
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                             : "r"(lane_base + b * BN + (unsigned)c));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum[c + j] = fmaf(__uint_as_float(v[j]), 1.00000012f, sum[c + j]);   // chain of 4: see header
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&accfree[b]);
+        };
+        for (int i = 0; i < count; ++i) {
+            const int s = i % kTcStages;
+            mbar_wait(&full[s], ((unsigned)(i / kTcStages)) & 1u);
+            float4* st = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
+            constexpr int a4 = a_bytes / 16, b4 = b_bytes / 16;
+            for (int e = t; e < a4 + b4; e += 128) {
+                float4* hi = e < a4 ? st + e : st + 2 * a4 + (e - a4);
+                float4* lo = e < a4 ? hi + a4 : hi + b4;
+                const float4 x = *hi;
+                float4 h, l;
+                h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
+                h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
+                h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
+                h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
+                *hi = h;
+                *lo = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&conv[s]);
+            if (i > 0) drain(i - 1);                                     // the previous stage's MMAs run meanwhile
+        }
+        if (count > 0) drain(count - 1);
+        // the last commit also covered the correction accumulator
+#pragma unroll
+        for (int c = 0; c < BN; c += 16) {
+            unsigned v[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                         : "r"(lane_base + 2 * BN + (unsigned)c));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) sum[c + j] += __uint_as_float(v[j]);
+        }
+        const int row = m0 + q * 32 + lane;
+        if (row < a.M) {
+            float* out = a.partials + ((size_t)blockIdx.z * a.M + row) * a.N + n0;
+#pragma unroll
+            for (int c = 0; c < BN; ++c)
+                if (n0 + c < a.N) out[c] = sum[c];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kCols));
+    }
+}
+
 // dst[c][r] = src[r][c]   (32x32 tiles through shared memory)
 __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
     __shared__ float tile[32][33];
@@ -257,6 +407,32 @@ int transpose(const float* src, float* dst, int R, int C, cudaStream_t st) {
 
 // partials[z][M][N] = A[M, kz] . B[N, kz]^T for every K split z.  Returns the number of splits (>= 1) on success, 0 on
 // a launch error (paig_last_error), -1 when the shape does not qualify (caller uses the CUDA-core GEMM).
+// Drained variant (see gemm_tf32x3_drained_kernel): N tiled by 112 or 96 columns, fixed K split of 12 blocks.
+int gemm_tc_partials_drained(const float* A, const float* B, int M, int N, int K, float* partials, size_t partial_floats,
+                             const char* tag, cudaStream_t st) {
+    static const bool off = getenv("PAIG_NO_TCGEN05") != nullptr;
+    if (off || M < 128 || N < 96 || K < 128) return -1;
+    if ((K % 4) != 0 || ((uintptr_t)A % 16) || ((uintptr_t)B % 16)) return -1;
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = M; a.N = N; a.K = K;
+    a.BN = (N % 112 == 0 || N > 96) ? 112 : 96;
+    const int nkb = cdiv(K, kTcBK);
+    int splits = nkb >= 24 ? nkb / 12 : 1;                               // by K only: batch-invariant summation order
+    while (splits > 1 && (size_t)splits * M * N > partial_floats) --splits;
+    if ((size_t)splits * M * N > partial_floats) return -1;
+    a.kb_per = cdiv(nkb, splits);
+    splits = cdiv(nkb, a.kb_per);
+    a.partials = partials;
+    if (!tc_map(&a.tmA, A, M, K, kTcBM) || !tc_map(&a.tmB, B, N, K, a.BN)) return -1;
+    const size_t smem = (size_t)kTcStages * (2 * kTcBM * 128 + 2 * (size_t)a.BN * 128) + 1024;
+    const dim3 grid(cdiv(N, a.BN), cdiv(M, kTcBM), splits);
+    if (a.BN == 112) launch(gemm_tf32x3_drained_kernel<112>, grid, dim3(kTcThreads), smem, st, a);
+    else launch(gemm_tf32x3_drained_kernel<96>, grid, dim3(kTcThreads), smem, st, a);
+    if (check_launch(tag ? tag : "gemm_tf32x3_drained")) return 0;
+    return splits;
+}
+
 int gemm_tc_partials(const float* A, const float* B, int M, int N, int K, bool fixed_split, float* partials,
                      size_t partial_floats, const char* tag, cudaStream_t st) {
     static const bool off = getenv("PAIG_NO_TCGEN05") != nullptr;
@@ -291,6 +467,7 @@ int gemm_tc_partials(const float* A, const float* B, int M, int N, int K, bool f
 namespace paig {
 int transpose(const float*, float*, int, int, cudaStream_t) { return 1; }
 int gemm_tc_partials(const float*, const float*, int, int, int, bool, float*, size_t, const char*, cudaStream_t) { return -1; }
+int gemm_tc_partials_drained(const float*, const float*, int, int, int, float*, size_t, const char*, cudaStream_t) { return -1; }
 }  // namespace paig
 
 #endif

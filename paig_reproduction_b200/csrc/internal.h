@@ -151,6 +151,9 @@ int gemm_fold_partials(const GemmArgs& g, int splits, cudaStream_t st);
 // gemm_tc.cu -- 3xTF32 tcgen05 GEMM for K-major operands; see the file header for the return convention
 int gemm_tc_partials(const float* A, const float* B, int M, int N, int K, bool fixed_split, float* partials,
                      size_t partial_floats, const char* tag, cudaStream_t st);
+// short accumulation chains + truncation compensation: for products that feed activations (encoder.l1 forward)
+int gemm_tc_partials_drained(const float* A, const float* B, int M, int N, int K, float* partials, size_t partial_floats,
+                             const char* tag, cudaStream_t st);
 int transpose(const float* src, float* dst, int R, int C, cudaStream_t st);
 int linear_forward(const float* X, const float* W, const float* b, float* Y, int M, int K, int N, int epi,
                    cudaStream_t st, float* splitk_ws = nullptr, size_t splitk_floats = 0, const char* tag = nullptr);

@@ -375,8 +375,10 @@ int paig_velocity_backward(const paig_task* t, const paig_params* p, const paig_
 
 int paig_debug_gemm_tc(const float* A, const float* B, float* C, int M, int N, int K, int fixed_split, float* scratch,
                        long scratch_floats, void* stream) {
-    const int sp = gemm_tc_partials(A, B, M, N, K, fixed_split != 0, scratch, (size_t)scratch_floats, "gemm_tf32x3",
-                                    (cudaStream_t)stream);
+    const int sp = fixed_split == 2
+        ? gemm_tc_partials_drained(A, B, M, N, K, scratch, (size_t)scratch_floats, "gemm_tf32x3_drained", (cudaStream_t)stream)
+        : gemm_tc_partials(A, B, M, N, K, fixed_split != 0, scratch, (size_t)scratch_floats, "gemm_tf32x3",
+                           (cudaStream_t)stream);
     if (sp < 0) { set_error("gemm_tc: shape %d x %d x %d does not qualify", M, N, K); return 1; }
     if (sp == 0) return 2;
     GemmArgs g;

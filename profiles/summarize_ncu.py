@@ -19,6 +19,9 @@ COLS = [
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma pipe %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe %"),
+    ("sm__pipe_tensor_subpipe_utc_cycles_active.avg.pct_of_peak_sustained_active", "tcgen05 (UTC) pipe %"),
+    ("sm__inst_executed_pipe_tensor.sum", "tensor insts"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smem wavefront %"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "bank conflicts"),
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),

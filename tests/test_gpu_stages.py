@@ -130,6 +130,9 @@ def test_conv3x3_forward_beyond_65535_frame_groups():
     (200, 3072, 2000, 0),      # weight gradient: dH1^T[200, nN] . A^T[K, nN]^T
     (2000, 3072, 200, 0),      # data gradient:   dH1[nN, 200] . W1^T[K, 200]^T
     (260, 200, 3072, 1),       # a ragged M (13 sequences x 10 frames x 2 objects): partial last row tile
+    (2000, 200, 3072, 2),      # encoder.l1 forward as the step runs it: drained accumulation chains (fixed = 2)
+    (3200, 200, 3888, 2),
+    (260, 200, 3072, 2),
 ])
 def test_tcgen05_gemm_tf32x3_vs_fp64(M, N, K, fixed):
     """csrc/gemm_tc.cu through its test hook: C = A . B^T as hi*hi + hi*lo + lo*hi on tcgen05 (K-major operands, TMA
@@ -155,6 +158,16 @@ def test_tcgen05_gemm_tf32x3_vs_fp64(M, N, K, fixed):
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
     assert err < 5e-6, (err, err_blas)                      # single-pass TF32 would sit near 5e-4
+    if fixed == 2:
+        # the point of the drained kernel: no coherent shrink.  Same-sign operands make a truncating accumulator's
+        # bias visible as a mean signed relative error (one accumulation chain per split: about -2e-6)
+        Ap, Bp = A.abs() + 0.05, B.abs() + 0.01
+        _lib.check(lib.paig_debug_gemm_tc(Ap.data_ptr(), Bp.data_ptr(), C.data_ptr(), M, N, K, 2, scratch.data_ptr(),
+                                          scratch.numel(), st), "gemm_tc")
+        torch.cuda.synchronize()
+        refp = Ap.double() @ Bp.double().t()
+        bias = ((C.double() - refp) / refp).mean().item()
+        assert abs(bias) < 6e-8, bias
     # the same product again: bit-identical (fixed summation order)
     C2 = torch.empty_like(C)
     _lib.check(lib.paig_debug_gemm_tc(A.data_ptr(), B.data_ptr(), C2.data_ptr(), M, N, K, fixed, scratch.data_ptr(),
