@@ -55,7 +55,7 @@ struct ConvTcArgs {
     int fpt;                  // frames per tile (1, or 2 at S = 8)
     int tiles_x, tpg;         // tiles per row, tiles per frame group
     int ntiles, nsuper, drain;
-    float comp;               // != 0: truncation-bias compensation of the drained partials (see the epilogue)
+    float comp;               // expected relative truncation loss of a drained partial, added back in the epilogue (0: off)
     int dbg;                  // timing experiments (PAIG_CONV_TC_DBG): 1 skip patch conversion, 2 skip weight split, 4 skip MMAs, 8 skip drains
 };
 
@@ -113,6 +113,13 @@ __device__ __forceinline__ void ct_ld16(unsigned taddr, unsigned (&v)[16]) {
                    "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ void ct_ld16_nowait(unsigned taddr, unsigned (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
 }
 
 // tile index -> frame group, first image row / column of the tile
@@ -313,30 +320,26 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv3x3_tc_kernel(const __grid_
                     const unsigned b = un % NB, use = un / NB;
                     ct_wait(&accfull[b], use & 1u);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    float mul = 1.f;
-                    if (a.comp != 0.f) {
-                        if (DRAIN == 9) mul = 1.00000024f;
-                        else if (DRAIN == 3) mul = g < 2 ? 1.00000012f : 1.f;
-                        else mul = (g % 4 == 0) ? 1.00000012f : 1.f;
-                    }
                     if (!(a.dbg & 8)) {
 #pragma unroll
                         for (int t = 0; t < T; ++t)
 #pragma unroll
-                            for (int c = 0; c < N; c += 16) {
-                                unsigned v[16];
-                                ct_ld16(lane_base + (b * T + t) * N + c, v);
-                                // The tensor core truncates (round toward zero) when it aligns the 8 products of an
-                                // MMA and again when it adds them to the fp32 accumulator: every drained partial is
-                                // short by an EXPECTED ~0.28 / 0.62 / 2.1 x 2^-23 of itself for chains of 1 / 3 / 9
-                                // accumulations (measured on same-sign operands, profiles/r2d_conv_tc_sweep.txt) -- a
-                                // coherent shrink that a long ReLU network amplifies into the gradients.  The expected
-                                // loss is added back inside the SAME fused multiply-add that accumulates the partial
-                                // (sum = partial x (1 + k 2^-23) + sum, rounded once, so the correction is not lost to
-                                // the rounding of the much larger running sum); 2^-23 being the finest factor fp32 can
-                                // express, chains of 3 take it on 2 of 3 drains and chains of 1 on 3 of 9.
+                            for (int c = 0; c < N; c += 32) {
+                                if (c + 32 <= N) {                  // two loads in flight per wait
+                                    unsigned v[16], u[16];
+                                    ct_ld16_nowait(lane_base + (b * T + t) * N + c, v);
+                                    ct_ld16_nowait(lane_base + (b * T + t) * N + c + 16, u);
+                                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) sum[t][c + j] = fmaf(__uint_as_float(v[j]), mul, sum[t][c + j]);
+                                    for (int j = 0; j < 16; ++j) sum[t][c + j] += __uint_as_float(v[j]);
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) sum[t][c + 16 + j] += __uint_as_float(u[j]);
+                                } else {
+                                    unsigned v[16];
+                                    ct_ld16(lane_base + (b * T + t) * N + c, v);
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) sum[t][c + j] += __uint_as_float(v[j]);
+                                }
                             }
                     }
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -350,8 +353,18 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv3x3_tc_kernel(const __grid_
                 for (int c = 0; c < N; c += 16) {
                     unsigned v[16];
                     ct_ld16(lane_base + (NB * T + t) * N + c, v);
+                    // The tensor core truncates (round toward zero) the sum of an MMA's 8 products and its fp32 accumulator:
+                    // every drained partial is short by an EXPECTED kappa = 0.28 / 0.62 / 2.1 x 2^-23 of itself for chains
+                    // of 1 / 3 / 9 accumulations (measured, profiles/r2d_conv_tc_sweep.txt).  With one MMA per drained
+                    // partial (DRAIN = 1) the loss is proportional to each partial whatever its sign, so the sum of the
+                    // partials is short by kappa x itself -- a coherent shrink of every pre-activation that a deep ReLU
+                    // network amplifies ~1000x into the gradients (mnist_spring_color B = 100 fails the parity bar
+                    // without it).  It is added back once, next to the small hi.lo + lo.hi correction, BEFORE the one
+                    // round-to-nearest addition to the sum: kappa x sum is below half an ulp of sum, on its own it would
+                    // always round away.  (Scaling single partials by 1 + 2^-23, the finest factor fp32 has, on a subset
+                    // of the taps was measured too: it distorts the taps against each other and made parity worse.)
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) sum[t][c + j] += __uint_as_float(v[j]);
+                    for (int j = 0; j < 16; ++j) sum[t][c + j] += fmaf(sum[t][c + j], a.comp, __uint_as_float(v[j]));
                 }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             ct_arrive(&corrfree);
@@ -434,16 +447,21 @@ int ct_sm_count() {
 // Taps whose hi.hi products share one TMEM accumulation chain.  Measured (profiles/r2d_conv_tc_sweep.txt, all-positive
 // operands) mean signed relative error without compensation: -3e-8 / -7e-8 / -2.5e-7 for 1 / 3 / 9 (FMA kernel: 1e-9).
 // Forward convolutions feed ReLU stacks whose coherent shrink the position head amplifies ~1000x into the gradients:
-// they drain per tap row (3) and compensate.  Data gradients only get scaled by 1 - 2.5e-7: they drain per chunk (9).
+// uncompensated, or compensated tap by tap, the 64-px task misses the gradient bar at B = 100; with the expected loss of
+// the whole sum added back once in the epilogue, chains of 1 and of 3 both pass it below 1e-4 without the noise allowance
+// (profiles/r2m_parity_sweep*.txt).  They drain per tap row (3): 25.8 ms per mnist step against 27.6 with chains of 1.
+// Data gradients only get scaled by 1 - 2.5e-7 (compensated to ~0): they drain per chunk (9).
 int ct_drain(bool backward) {
     static const int f = getenv("PAIG_CONV_TC_DRAIN") ? atoi(getenv("PAIG_CONV_TC_DRAIN")) : 3;
     static const int b = getenv("PAIG_CONV_TC_DRAIN_BWD") ? atoi(getenv("PAIG_CONV_TC_DRAIN_BWD")) : 9;
     const int v = backward ? b : f;
     return v == 9 ? 9 : (v == 1 ? 1 : 3);
 }
-float ct_comp(int) {
+float ct_comp(int drain) {
     static const bool off = getenv("PAIG_CONV_TC_NOCOMP") != nullptr;
-    return off ? 0.f : 1.f;
+    static const float k1 = getenv("PAIG_CONV_TC_KAPPA") ? (float)atof(getenv("PAIG_CONV_TC_KAPPA")) : 0.28f;
+    const float ulp = 1.1920929e-7f;
+    return off ? 0.f : (drain == 1 ? k1 : (drain == 3 ? 0.62f : 2.1f)) * ulp;
 }
 
 template <int N, int T, bool F2>
@@ -480,6 +498,8 @@ int conv3x3_tc(const ConvArgs& c, float* scratch, cudaStream_t st) {
     static const int min_n = getenv("PAIG_CONV_TC_MIN_N") ? atoi(getenv("PAIG_CONV_TC_MIN_N")) : 32;
     if (N < min_n && !c.force_tc) return -1;
     if (S != 8 && S != 16 && S != 32 && S != 64) return -1;
+    static const int dirs = getenv("PAIG_CONV_TC_DIR") ? atoi(getenv("PAIG_CONV_TC_DIR")) : 3;   // bit 0 forward, bit 1 data gradient
+    if (!(dirs & (c.transposed ? 2 : 1)) && !c.force_tc) return -1;
     if (((uintptr_t)c.in % 16) || (c.in_bs % 4) || c.N <= 0) return -1;
     CtEncodeFn enc = ct_encode_fn();
     if (!enc) return -1;
