@@ -61,6 +61,7 @@ struct FusedPlan {
     const float* x;
     const float* wpack;
     long long* timing;             // debug (PAIG_DEBUG): per-CTA cycle stamps after every op of the CTA's first frames
+    float kappa;                   // tensor-core variant: expected relative truncation loss of one MMA, added back in the epilogue
     FusedOp ops[kFusedMaxOps];
 };
 
@@ -395,6 +396,239 @@ __device__ __forceinline__ void run_conv_co(const FusedOp& op, float* sm, int f,
     else run_conv<4, COUT, 1>(op, sm, f, tid, tm);
 }
 
+
+// ---- tensor-core variant of the accumulate loop (32-px frames: levels of 32, 16 and 8 px) ------------------------------
+// The same convolutions as implicit GEMMs on the warp-level tensor-core path (mma.sync.m16n8k8, SASS HMMA.1688.F32.TF32),
+// fp32-accurate through the 3xTF32 split (x = hi + lo, hi = rn_tf32(x), lo = rn_tf32(x - hi); a.b ~ hi.hi + hi.lo + lo.hi):
+//
+//     D[co, px] = sum_{tap, ci} W[co, ci, tap] * in[ci, px + tap]        M = 16 output channels, N = 8 pixels of a row, K = 8 input channels
+//
+// Why mma.sync and not tcgen05 here: with 8..32 output channels a tcgen05.mma (M = 128 pixels) reads a 4 KB pixel slab from
+// shared memory per K = 8 step whatever N is, which is what bounds it (conv_tc.cu at N = 16: a tie with the FMA loop,
+// profiles/r2k_conv_tc_sweep.txt) and it needs the activations re-laid out as hi and lo tiles -- twice the footprint of a
+// frame that fills the SM already.  The warp-level path takes the B fragments straight out of the existing [C][S+2][P]
+// planes (lane (g, t) reads channel t / t+4 at pixel g: 4 planes x 8 consecutive floats = 32 distinct banks because
+// plane = 8 or 24 (mod 32) at S = 32 / 16 / 8), splits them in registers, and keeps the weights of one tap in 8 registers
+// for all the n-tiles of the warp.  Measured rate: 512 MAC/clk/SM (tools/ubench/mma_sync_rate.cu), i.e. 170 useful
+// MAC/clk/SM after the split against the ~55 the FMA loop reaches (it is bound by shared-memory wavefronts: 9.3 per
+// 1024 MAC; this loop needs 2).
+//
+// Accuracy: the tensor core sums the 8 products of an MMA with truncation.  hi.hi goes through an MMA with a ZERO
+// accumulator and is added to a register sum with round-to-nearest (no accumulation chain inside the tensor core); the
+// expected truncation loss of one MMA (kappa x result, see conv_tc.cu) is added back once, next to the small correction
+// sum (hi.lo + lo.hi, accumulated inside the MMA), before the single final addition.
+#ifndef PAIG_EMU
+// hi = x rounded to TF32 (10 mantissa bits), nearest with ties away from zero -- what cvt.rna.tf32.f32 computes, but that
+// instruction is emulated on sm_100a (FSETP + SEL + LOP3 + IADD, ~2.5 issue slots and it was a third of the loop);
+// on the bit pattern it is one add and one mask (finite inputs).  lo = x - hi is exact in fp32 and goes to the tensor
+// core as it is: the MMA reads only the upper 19 bits of a TF32 operand, a truncation of a term that is 2^-12 of x
+// with a random sign.
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void mma_tf32_acc(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ void mma_tf32_zero(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)), "f"(0.f));
+}
+
+template <int S> struct MmaGeo {
+    static constexpr int P = 4 * ((S + 3) / 4) + 4, PLANE = (S + 2) * P;
+    static constexpr int TPR = S / 8;                         // n-tiles (8 pixels) per image row
+    static constexpr int NT = S == 32 ? 4 : (S == 16 ? 2 : 1);   // n-tiles per warp and pass: one image row
+    // correction accumulators per n-tile.  An accumulating HMMA needs the previous one on the same registers to have
+    // finished (~33 cycles): hi.lo and lo.hi go to separate accumulators, and with fewer than 4 n-tiles per warp even
+    // and odd taps alternate between two pairs, so that dependent MMAs are >= 6 MMA slots (48 cycles) apart
+    static constexpr int SETS = NT >= 4 ? 2 : 4;               // (the two-row upsampling conv at 32 px has registers for 1 only)
+};
+
+// One K range (nkc chunks of 8 input channels starting at `planes`) into the warp's NT n-tiles of m-tile `mt`.
+// pb: planes + t * PLANE + row * P + g (lane part folded in).  wf: the lane's float4 of chunk 0 / tap 0 / m-tile mt.
+template <int S, int SETS>
+__device__ __forceinline__ void conv_accumulate_mma(float (&sum)[MmaGeo<S>::NT][4], float (&corr)[MmaGeo<S>::NT][SETS][4],
+                                                    const float* __restrict__ pb, int nkc, const float4* __restrict__ wf,
+                                                    int wtap /* float4s between taps */) {
+    constexpr int P = MmaGeo<S>::P, PLANE = MmaGeo<S>::PLANE, NT = MmaGeo<S>::NT;
+#pragma unroll 1
+    for (int kc = 0; kc < nkc; ++kc) {
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const int ky = tap / 3, kx = tap % 3;
+            const float4 w4 = wf[tap * wtap];
+            float ah[4], al[4];
+            ah[0] = tf32_hi(w4.x); al[0] = w4.x - ah[0];
+            ah[1] = tf32_hi(w4.y); al[1] = w4.y - ah[1];
+            ah[2] = tf32_hi(w4.z); al[2] = w4.z - ah[2];
+            ah[3] = tf32_hi(w4.w); al[3] = w4.w - ah[3];
+            constexpr int kAlt = SETS == 4 ? 2 : 0, kSecond = SETS >= 2 ? 1 : 0;
+            const int set = (tap & 1) * kAlt;
+            float d[NT][4], h0[NT], h1[NT], l0[NT], l1[NT];
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                const float* q = pb + ky * P + nt * 8 + kx;
+                const float b0 = q[0], b1 = q[4 * PLANE];
+                h0[nt] = tf32_hi(b0); h1[nt] = tf32_hi(b1);
+                l0[nt] = b0 - h0[nt]; l1[nt] = b1 - h1[nt];
+                mma_tf32_zero(d[nt], ah, h0[nt], h1[nt]);
+            }
+            // (issue order: the two accumulating MMAs of an n-tile are NT slots apart even when they share registers)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32_acc(corr[nt][set], ah, l0[nt], l1[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) mma_tf32_acc(corr[nt][set + kSecond], al, h0[nt], h1[nt]);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+                sum[nt][0] += d[nt][0]; sum[nt][1] += d[nt][1]; sum[nt][2] += d[nt][2]; sum[nt][3] += d[nt][3];
+            }
+        }
+        pb += 8 * PLANE;
+        wf += 9 * wtap;
+    }
+}
+
+template <int S, int SETS>
+__device__ __forceinline__ void mma_epilogue(float (&sum)[MmaGeo<S>::NT][4], const float (&corr)[MmaGeo<S>::NT][SETS][4],
+                                             const FusedOp& op, float* sm, const float* bias, int mt, int y, int g, int t,
+                                             int f, float kappa) {
+    constexpr int P = MmaGeo<S>::P, PLANE = MmaGeo<S>::PLANE, NT = MmaGeo<S>::NT;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float c = corr[nt][0][i];
+            if (SETS >= 2) c += corr[nt][1][i];
+            if (SETS == 4) c += corr[nt][2][i] + corr[nt][3][i];
+            sum[nt][i] += fmaf(sum[nt][i], kappa, c);                                        // (the corrections die here)
+        }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int co = mt * 16 + g + 8 * h;
+        if (co >= op.Cout) continue;                               // 8-channel layers: rows 8..15 of the m-tile are padding
+        float2 gate[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {                          // the gate loads go out before the first store
+            gate[nt] = make_float2(1.f, 1.f);
+            if (op.gmask)
+                gate[nt] = *reinterpret_cast<const float2*>(op.gmask + (long)f * op.gmask_bs + ((long)co * S + y) * S + nt * 8 + 2 * t);
+        }
+        const float b = op.bias ? bias[co] : 0.f;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int x = nt * 8 + 2 * t;
+            float v0 = sum[nt][2 * h] + b, v1 = sum[nt][2 * h + 1] + b;
+            if (op.relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
+            v0 = gate[nt].x > 0.f ? v0 : 0.f;
+            v1 = gate[nt].y > 0.f ? v1 : 0.f;
+            if (op.out >= 0) {
+                float* d = sm + op.out + co * PLANE + (y + 1) * P + x + 1;
+                d[0] = v0; d[1] = v1;
+            }
+            if (op.gout)
+                *reinterpret_cast<float2*>(op.gout + (long)f * op.gout_bs + ((long)co * S + y) * S + x) = make_float2(v0, v1);
+        }
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void run_conv_mma(const FusedOp& op, float* sm, int f, int tid, float kappa, long long* tm) {
+    constexpr int P = MmaGeo<S>::P, PLANE = MmaGeo<S>::PLANE, NT = MmaGeo<S>::NT, SETS = MmaGeo<S>::SETS;
+    const Geo geo = geo_of(S);
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int mtiles = (op.Cout + 15) >> 4;
+    const int kc0 = (op.Cin0 + 7) >> 3, kc1 = op.Cin1 >> 3;
+    const float4* w = reinterpret_cast<const float4*>(sm + op.wsm);
+    const float* bias = sm + op.wsm + (kc0 + kc1) * 9 * mtiles * 128;
+    if (op.out >= 0) zero_halo_planes(sm + op.out, op.Cout, geo, tid, kFusedThreads);
+    PAIG_STAMP(tm, 1);
+    // a warp item = (m-tile, image row): S * mtiles items over the 16 warps, m-tile the slowest index
+    const int nitems = S * mtiles;
+    const int wtap = mtiles * 32;
+    float sum[NT][4], corr[NT][SETS][4];
+    if (!op.up) {
+        for (int item = warp; item < nitems; item += kFusedThreads / 32) {
+            const int mt = item / S, y = item - mt * S;
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    sum[nt][i] = 0.f;
+#pragma unroll
+                    for (int q = 0; q < SETS; ++q) corr[nt][q][i] = 0.f;
+                }
+            if (op.gmask) {
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        if (mt * 16 + g + 8 * h < op.Cout)
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(op.gmask + (long)f * op.gmask_bs +
+                                         ((long)(mt * 16 + g + 8 * h) * S + y) * S + nt * 8 + 2 * t));
+            }
+            const float4* wf = w + mt * 32 + lane;
+            conv_accumulate_mma<S, SETS>(sum, corr, sm + op.in0 + t * PLANE + y * P + g, kc0, wf, wtap);
+            if (kc1) conv_accumulate_mma<S, SETS>(sum, corr, sm + op.in1 + t * PLANE + y * P + g, kc1, wf + kc0 * 9 * wtap, wtap);
+            mma_epilogue<S, SETS>(sum, corr, op, sm, bias, mt, y, g, t, f, kappa);
+        }
+        PAIG_STAMP(tm, 2);
+        PAIG_STAMP(tm, 3);
+    } else {
+        // upsample fused into the conv: 8 channels (one K chunk) are built at a time.  One m-tile (planner); at S = 32 a
+        // warp owns two rows, whose accumulators both persist across the chunks.
+        constexpr int R = S >= 32 ? 2 : 1;                         // rows per warp: 2 at 32 px, 1 at 16 px (8 px: planner refuses)
+        constexpr int US = R == 2 ? 1 : SETS;
+        float sum2[R][NT][4], corr2[R][NT][US][4];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    sum2[r][nt][i] = 0.f;
+#pragma unroll
+                    for (int q = 0; q < US; ++q) corr2[r][nt][q][i] = 0.f;
+                }
+        const Geo gl = geo_of(S / 2);
+        float* chunk = sm + op.chunk;
+        zero_halo_planes(chunk, 8, geo, tid, kFusedThreads);
+        for (int c0 = 0; c0 < op.Cin0; c0 += 8) {
+            upsample_chunk(sm + op.in0 + c0 * gl.plane, gl, chunk, geo, 8,
+                           op.gup ? op.gup + (long)f * op.gup_bs + (long)c0 * S * S : nullptr, tid);
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                conv_accumulate_mma<S, US>(sum2[r], corr2[r], chunk + t * PLANE + (warp + 16 * r) * P + g, 1,
+                                       w + lane + (c0 >> 3) * 9 * wtap, wtap);
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) mma_epilogue<S, US>(sum2[r], corr2[r], op, sm, bias, 0, warp + 16 * r, g, t, f, kappa);
+    }
+    (void)sum; (void)corr;
+}
+#endif   // !PAIG_EMU
+
+template <bool MMA>
+__device__ __forceinline__ void run_conv_any(const FusedOp& op, float* sm, int f, int tid, float kappa, long long* tm) {
+#ifndef PAIG_EMU
+    if (MMA) {
+        if (op.S == 32) run_conv_mma<32>(op, sm, f, tid, kappa, tm);
+        else if (op.S == 16) run_conv_mma<16>(op, sm, f, tid, kappa, tm);
+        else run_conv_mma<8>(op, sm, f, tid, kappa, tm);
+        return;
+    }
+#endif
+    (void)kappa;
+    if (op.Cout == 8) run_conv_co<8>(op, sm, f, tid, tm);
+    else if (op.Cout == 16) run_conv_co<16>(op, sm, f, tid, tm);
+    else run_conv_co<32>(op, sm, f, tid, tm);
+}
+
+template <bool MMA>
 __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const FusedPlan P) {
     PAIG_DYN_SMEM(float, sm);
     __shared__ unsigned long long bars[2];
@@ -424,6 +658,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const 
         // ---- the input frame, zero halo ----
         float* X = sm + P.x_off;
         zero_halo_planes(X, 3, gx, tid, kFusedThreads);
+        if (MMA)                              // the first conv's K chunk is 8 channels wide: planes 3..7 are zeros
+            for (int e = tid; e < 5 * gx.plane; e += kFusedThreads) X[3 * gx.plane + e] = 0.f;
         const float* xf = P.x + (long)(f / P.fps) * P.seq_stride + (long)(f % P.fps) * 3 * HW;
         if ((P.H & 3) == 0) {
             const int rowq = P.H / 4;
@@ -459,9 +695,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_fwd_kernel(const 
             }
             PAIG_STAMP(tm, 0);
             if (op.kind == F_CONV) {
-                if (op.Cout == 8) run_conv_co<8>(op, sm, f, tid, tm);
-                else if (op.Cout == 16) run_conv_co<16>(op, sm, f, tid, tm);
-                else run_conv_co<32>(op, sm, f, tid, tm);
+                run_conv_any<MMA>(op, sm, f, tid, P.kappa, tm);
             } else if (op.kind == F_POOL) {
                 const int So = op.S, C = op.Cin0;
                 const Geo go = geo_of(So), gi = geo_of(2 * So);
@@ -598,7 +832,6 @@ __device__ __forceinline__ void run_poolT(const FusedOp& op, float* sm, int f, i
                 const int toff[4] = {t00, t00 + 1, t00 + gx.P, t00 + gx.P + 1};
                 const long g00 = (long)f * op.gout_bs + ((long)c * Si + 2 * y) * Si + 2 * x;
                 const long goff[4] = {g00, g00 + 1, g00 + Si, g00 + Si + 1};
-#pragma unroll
                 const float parked[4] = {pa[u].x, pa[u].y, pb[u].x, pb[u].y};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -657,6 +890,7 @@ __device__ __forceinline__ void run_headT(const FusedOp& op, float* sm, int f, i
 // Backward-data pass of the whole UNet for one frame at a time: the gradient of every conv output, already gated by
 // that layer's ReLU, goes to the workspace (where the weight-gradient kernels read it) and stays on chip for the
 // next transposed conv.  Same CTA shape, planner and weight pipeline as the forward kernel.
+template <bool MMA>
 __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_bwd_kernel(const FusedPlan P) {
     PAIG_DYN_SMEM(float, sm);
     __shared__ unsigned long long bars[2];
@@ -700,9 +934,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_bwd_kernel(const 
             }
             PAIG_STAMP(tm, 0);
             if (op.kind == F_CONV) {
-                if (op.Cout == 8) run_conv_co<8>(op, sm, f, tid, tm);
-                else if (op.Cout == 16) run_conv_co<16>(op, sm, f, tid, tm);
-                else run_conv_co<32>(op, sm, f, tid, tm);
+                run_conv_any<MMA>(op, sm, f, tid, P.kappa, tm);
             } else if (op.kind == F_UPT) {
                 run_upT(op, sm, f, tid);
             } else if (op.kind == F_POOLT) {
@@ -728,6 +960,9 @@ struct PackPlan {
                        //    dst[(co*9 + tap)*Cout + c] = W[co][ci0 + c][8 - tap]   (Cin = number of co, no bias)
     int ci0[24], cin_total[24];
     long off[24];
+    int frag;          // tensor-core variant: 3x3 layers go out in mma.sync A-fragment order
+                       //    dst[(((kc*9 + tap)*mtiles + mt)*32 + lane)*4 + j] = W[co = 16mt + lane/4 + 8(j&1)][ci = 8kc + lane%4 + 4(j>>1)][tap]
+                       //    (zero beyond Cout / Cin), bias after the last fragment
 };
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackPlan P, float* __restrict__ dst) {
     const int l = blockIdx.y;
@@ -735,6 +970,24 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackPlan P, flo
     const int Cout = P.Cout[l], Cin = P.Cin[l], taps = P.taps[l];
     const int nW = Cout * Cin * taps;
     float* d = dst + P.off[l];
+    if (P.frag && taps == 9) {
+        const int mtiles = (Cout + 15) >> 4, nkc = (Cin + 7) >> 3;
+        const int nF = nkc * 9 * mtiles * 128;
+        const bool tr = P.mode[l] == 1;
+        for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nF + (tr ? 0 : Cout); e += gridDim.x * blockDim.x) {
+            if (e >= nF) { d[e] = P.b[l][e - nF]; continue; }
+            const int j = e & 3, lane = (e >> 2) & 31;
+            int r = e >> 7;
+            const int mt = r % mtiles; r /= mtiles;
+            const int tap = r % 9, kc = r / 9;
+            const int co = mt * 16 + (lane >> 2) + ((j & 1) ? 8 : 0), ci = kc * 8 + (lane & 3) + ((j & 2) ? 4 : 0);
+            float v = 0.f;
+            if (co < Cout && ci < Cin)
+                v = tr ? P.w[l][((long)ci * P.cin_total[l] + P.ci0[l] + co) * 9 + (8 - tap)] : P.w[l][((long)co * Cin + ci) * 9 + tap];
+            d[e] = v;
+        }
+        return;
+    }
     if (P.mode[l] == 2) {                                    // head weights as they are, no bias
         for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nW; e += gridDim.x * blockDim.x) d[e] = P.w[l][e];
         return;
@@ -844,6 +1097,26 @@ bool choose_tile(FusedOp& fo, bool single_pass) {
     return true;
 }
 
+// Tensor-core variant of the fused kernels (mma.sync 3xTF32, see run_conv_mma): 32-px frames only (every level a multiple of
+// 8 pixels wide, plane strides of 8 / 24 mod 32 banks).  PAIG_FUSED_MMA=1 selects it.
+bool fused_mma_enabled(int H) {
+#ifdef PAIG_EMU
+    (void)H;
+    return false;
+#else
+    // measured (profiles/r2n_*): the HMMA pipe (one m16n8k8 per 8 cycles and scheduler) plus the split arithmetic leaves
+    // the variant at 0.81 / 0.78 ms against 0.71 / 0.79 ms for the FMA loops on spring_color -- opt-in until it wins
+    static const bool on = getenv("PAIG_FUSED_MMA") != nullptr && getenv("PAIG_NO_MMA") == nullptr;
+    return on && H == 32;
+#endif
+}
+float fused_mma_kappa() {
+    static const float k = getenv("PAIG_MMA_KAPPA") ? (float)atof(getenv("PAIG_MMA_KAPPA")) : 0.20f;
+    return k * 1.1920929e-7f;
+}
+inline int pad8(int c) { return (c + 7) & ~7; }
+inline int pad16(int c) { return (c + 15) & ~15; }
+
 int sm_count() {
 #ifdef PAIG_EMU
     return 2;
@@ -863,10 +1136,11 @@ int sm_count() {
 
 size_t unet_wpack_floats(const UNetDesc& u, const paig_task* t) {
     (void)t;
-    size_t total = 24 * 64;      // forward and backward-data packings, each entry padded to 256 bytes
+    size_t total = 48 * 64;      // forward and backward-data packings, each entry padded to 256 bytes
     for (int i = 0; i < u.nops; ++i) {
         const Op& op = u.ops[i];
-        if (op.kind == OP_CONV) total += align64((size_t)op.in.C * 9 * op.out.C + op.out.C);
+        // (fragment order of the tensor-core variant pads K to 8 and M to 16 channels, per concat slice in backward)
+        if (op.kind == OP_CONV) total += align64((size_t)(pad8(op.in.C) + 16) * 9 * pad16(op.out.C) + op.out.C);
         else if (op.kind == OP_HEAD) total += align64((size_t)op.in.C * op.out.C + op.out.C);
     }
     return 2 * total;
@@ -917,6 +1191,8 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
     memset(&K, 0, sizeof(K));
 
     for (int up_chunk = 8; up_chunk >= 2; up_chunk /= 2) {
+        bool mma = fused_mma_enabled(d.H) && up_chunk == 8;
+      replan:
         // ---- 1. fused op list (an UP is merged into the CONV that reads it) and the slices each op writes ----
         Slice sl[40];
         int ns = 0;
@@ -986,13 +1262,21 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
                 fo.Cout = op.out.C;
                 const int taps = op.kind == OP_CONV ? 9 : 1;
                 const int cin = fo.Cin0 + fo.Cin1;
-                fo.wfloats = (cin * taps * fo.Cout + fo.Cout + 3) & ~3;
+                size_t wf = (size_t)cin * taps * fo.Cout + fo.Cout;
+                if (mma && taps == 9) {
+                    // K chunks of 8 channels must not straddle the two concat segments; a narrower first segment is the
+                    // input frame (3 channels, zero planes behind it); an upsampling conv keeps one m-tile of accumulators
+                    if ((fo.Cin1 && (fo.Cin0 % 8 || fo.Cin1 % 8)) || (fo.Cin0 % 8 && a != 0) || (fo.up && fo.Cout > 16) ||
+                        (Sout != 32 && Sout != 16 && Sout != 8) || (fo.up && Sout < 16)) { mma = false; goto replan; }
+                    wf = (size_t)(pad8(cin) / 8) * 9 * (pad16(fo.Cout) / 16) * 128 + fo.Cout;
+                }
+                fo.wfloats = ((int)wf + 3) & ~3;
                 fo.wglob = woff;
                 fo.bias = 1;
                 K.w[nl] = p->conv[op.layer].w; K.b[nl] = p->conv[op.layer].b;
                 K.Cout[nl] = fo.Cout; K.Cin[nl] = cin; K.taps[nl] = taps; K.off[nl] = woff;
                 ++nl;
-                woff += (long)align64((size_t)cin * taps * fo.Cout + fo.Cout);
+                woff += (long)align64(wf);
                 if (fo.kind == F_CONV && fo.Cout != 8 && fo.Cout != 16 && fo.Cout != 32) { ok = false; break; }
             }
             if (op.kind == OP_HEAD) {
@@ -1017,10 +1301,12 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
             }
         }
         K.nlayers = nl;
+        K.frag = mma ? 1 : 0;
         P.nops = nf;
+        P.kappa = fused_mma_kappa();
         // ---- 2. thread tiling of each conv ----
         for (int k = 0; k < nf; ++k)
-            if (P.ops[k].kind == F_CONV && !choose_tile(P.ops[k], P.ops[k].up != 0)) return -1;
+            if (!mma && P.ops[k].kind == F_CONV && !choose_tile(P.ops[k], P.ops[k].up != 0)) return -1;
         // ---- 3. weight prefetch chain + barriers ----
         int prev = -1, widx = 0;
         P.first_w = -1;
@@ -1044,7 +1330,7 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
         }
         // ---- 4. shared-memory offsets by lifetime ----
         Planner al;
-        sl[0].floats = 3 * geo_of(d.H).plane;
+        sl[0].floats = (mma ? 8 : 3) * geo_of(d.H).plane;
         al.add(sl[0].floats, -1, sl[0].last, &sl[0].off);
         for (int k = 0; k < nf; ++k) {
             FusedOp& fo = P.ops[k];
@@ -1087,7 +1373,8 @@ int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L
 #ifndef PAIG_EMU
         P.timing = debug ? timing_buffer() : nullptr;
 #endif
-        launch(unet_fused_fwd_kernel, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
+        if (mma) launch(unet_fused_fwd_kernel<true>, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
+        else launch(unet_fused_fwd_kernel<false>, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
         (void)t;
         rc = check_launch("unet_fused_fwd");
 #ifndef PAIG_EMU
@@ -1115,6 +1402,7 @@ static int fused_backward_plan(const paig_task* t, const paig_params* p, const L
     memset(&P, 0, sizeof(P));
     PackPlan K;
     memset(&K, 0, sizeof(K));
+    const bool mma = fused_mma_enabled(d.H);
 
     // forward facts: who produced each slice, with a ReLU or not, and how many ops read it
     struct Prod { int buf, c0, C, op, kind, relu, readers; };
@@ -1244,11 +1532,16 @@ static int fused_backward_plan(const paig_task* t, const paig_params* p, const L
             FusedOp* fo = new_op(F_CONV);
             if (!fo) return -1;
             fo->S = side_of(op.out.buf); fo->Cin0 = op.out.C; fo->Cout = pr[k].C;
-            fo->wfloats = (op.out.C * 9 * pr[k].C + 3) & ~3;
+            size_t wf = (size_t)op.out.C * 9 * pr[k].C;
+            if (mma) {
+                if (op.out.C % 8 || (fo->S != 32 && fo->S != 16 && fo->S != 8)) return -1;
+                wf = (size_t)(op.out.C / 8) * 9 * (pad16(pr[k].C) / 16) * 128;
+            }
+            fo->wfloats = ((int)wf + 3) & ~3;
             fo->wglob = woff;
             K.w[nl] = p->conv[op.layer].w; K.b[nl] = nullptr; K.Cout[nl] = pr[k].C; K.Cin[nl] = op.out.C; K.taps[nl] = 9;
             K.mode[nl] = 1; K.ci0[nl] = pr[k].c0 - op.in.c0; K.cin_total[nl] = op.in.C; K.off[nl] = woff; ++nl;
-            woff += (long)align64((size_t)op.out.C * 9 * pr[k].C);
+            woff += (long)align64(wf);
             in0_of[nf] = ko; gs[ko].last = nf;
             if (via_up) {
                 // k is the upsampled tensor: keep its gradient on chip only, then gather it back to the source
@@ -1284,12 +1577,14 @@ static int fused_backward_plan(const paig_task* t, const paig_params* p, const L
     }
     if (nl > 24) return -1;
     K.nlayers = nl;
+    K.frag = mma ? 1 : 0;
     P.nops = nf;
+    P.kappa = fused_mma_kappa();
     for (int k = 0; k < npr; ++k)
         if (gs[k].parked) return -1;                     // a parked gradient nobody finalised
     // thread tiling of the transposed convs
     for (int k = 0; k < nf; ++k)
-        if (P.ops[k].kind == F_CONV && !choose_tile(P.ops[k], false)) return -1;
+        if (!mma && P.ops[k].kind == F_CONV && !choose_tile(P.ops[k], false)) return -1;
     // weight pipeline
     int issue_at[kFusedMaxOps];
     {
@@ -1342,7 +1637,8 @@ static int fused_backward_plan(const paig_task* t, const paig_params* p, const L
 #ifndef PAIG_EMU
     P.timing = debug ? timing_buffer() : nullptr;
 #endif
-    launch(unet_fused_bwd_kernel, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
+    if (mma) launch(unet_fused_bwd_kernel<true>, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
+    else launch(unet_fused_bwd_kernel<false>, dim3(grid), dim3(kFusedThreads), (size_t)peak * sizeof(float), st, P);
     (void)t;
     rc = check_launch("unet_fused_bwd");
 #ifndef PAIG_EMU

@@ -220,6 +220,178 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
     }
 }
 
+#ifndef PAIG_EMU
+// ---- tensor-core variant ---------------------------------------------------------------------------------------------
+// The same strips, the same barriers, the products on the warp-level tensor-core path (mma.sync.m16n8k8 TF32, SASS
+// HMMA.1688.F32.TF32) as a 3xTF32 split (a.b ~ hi.hi + hi.lo + lo.hi, see unet_fused.cu):
+//
+//     dW[co, ci](tap) += sum_px g[co, px] * in[ci, px + tap]         M = 16 output channels, N = 8 input channels, K = 8 pixels of a row
+//
+// A fragments come straight out of the g strip (lane (q, t): channel q / q+8, pixel t / t+4), B fragments out of the
+// input strip shifted by the tap (lane (q, t): channel q, pixel t + kx / +4) -- both conflict-free because pick_boxx puts
+// the channel planes 4 banks apart.  A warp owns one (16 co x 8 ci) block x 9 taps = 36 accumulators that live INSIDE the
+// MMA for a whole strip and are drained to a register sum once per strip (chains of <= ~50 truncating accumulations:
+// a relative loss of ~1e-6 of the partial, harmless for an end product compared at 1e-4; the forward/backward-data
+// convolutions, whose error is amplified by the network behind them, drain every MMA).  The g fragment of an 8-pixel
+// segment is split once and reused by 27 MMAs; per MMA the loop issues ~3 other instructions, against ~8 tensor-pipe
+// cycles: the kernel is bound by the tensor pipe (512 MAC/clk/SM, 170 after the split) where the FMA loop reached 47.
+// Pairs (m-tile, n-tile) x pixel partitions (rows r = part, part + P, ...) are dealt to the 8 warps; the host picks
+// channel blocks with at most 8 pairs.
+__device__ __forceinline__ float wg_tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+__device__ __forceinline__ void wg_mma(float (&d)[4], const float (&a)[4], float b0, float b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+          "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+__global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_mma_kernel(const __grid_constant__ WgradTmaArgs a) {
+    PAIG_DYN_SMEM(float, smem_raw);
+    __shared__ unsigned long long full[kWtMaxStages];
+    float* smem = smem_raw + (((128u - ((unsigned)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u) >> 2);
+    const int S = a.S, R = a.R, kWtStages = a.stages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, q = lane >> 2, t = lane & 3;
+    const int Cc = a.Cc, Oc = a.Oc;
+    const int c_base = ((int)blockIdx.y % a.csets) * Cc, o_base = ((int)blockIdx.y / a.csets) * Oc;
+    const int MT = (Oc + 15) >> 4, NTL = (Cc + 7) >> 3, G = MT * NTL;            // G <= 8 (host)
+    const int P = (kWtThreads / 32) / G;                                          // pixel partitions (rows)
+    const int pair = warp % G, part = warp / G;
+    const bool active = part < P;
+    const int mt = pair / NTL, nt = pair % NTL;
+    const int co0 = mt * 16 + q, co1 = co0 + 8, cil = nt * 8 + q;                 // local to the channel block
+    const bool v0 = co0 < Oc, v1 = co1 < Oc, vc = cil < Cc;
+
+    float acc[9][4], sum[9][4], bs0 = 0.f, bs1 = 0.f;
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[tp][i] = sum[tp][i] = 0.f;
+    const int items = a.N * a.strips;
+    const int n_my = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const unsigned stage_bytes = (unsigned)((Cc * a.in_plane + Oc * a.g_plane) * sizeof(float));
+    if (tid == 0) {
+        for (int s = 0; s < kWtMaxStages; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(&full[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int k) {                                          // thread 0 only
+        const int item = blockIdx.x + k * gridDim.x;
+        const int f = item / a.strips, y0 = (item % a.strips) * R;
+        float* st = smem + (size_t)(k % kWtStages) * a.stage_floats;
+        const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&full[k % kWtStages]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(stage_bytes) : "memory");
+        tma_box_load(st, &a.tm_in, a.vin, -4, y0 - 1, c_base, f, &full[k % kWtStages]);
+        tma_box_load(st + a.g_off, &a.tm_g, a.vg, 0, y0, o_base, f, &full[k % kWtStages]);
+    };
+    if (tid == 0)
+        for (int k = 0; k < kWtStages && k < n_my; ++k) issue(k);
+
+    const int bxi = a.vin.boxx, bxg = a.vg.boxx;
+    const int nseg = S >> 3;
+    for (int k = 0; k < n_my; ++k) {
+        const int item = blockIdx.x + k * gridDim.x;
+        const int y0 = (item % a.strips) * R;
+        const int rows = min(R, S - y0);
+        const float* sIn = smem + (size_t)(k % kWtStages) * a.stage_floats;
+        const float* sG = sIn + a.g_off;
+        {
+            const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&full[k % kWtStages]);
+            const unsigned phase = (unsigned)(k / kWtStages) & 1u;
+            unsigned done = 0;
+            while (!done)
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(done) : "r"(bar_a), "r"(phase) : "memory");
+        }
+        if (active) {
+            const float* g0 = sG + (v0 ? co0 : 0) * a.g_plane + t;
+            const float* g1 = sG + (v1 ? co1 : 0) * a.g_plane + t;
+            const float* xin = sIn + (vc ? cil : 0) * a.in_plane + t + 3;          // tile column = image column + 4, tap kx - 1
+            // units = (row, 8-pixel segment) dealt round-robin to the pixel partitions: 44 units over 8 partitions waste 8 %,
+            // whole rows (11 over 8) wasted 31 %
+            const int dr = P / nseg, ds = P % nseg;
+            int r = part / nseg, seg = part % nseg;
+            for (int u = part; u < rows * nseg; u += P) {
+                {
+                    const int x0 = seg * 8;
+                    float av[4];
+                    av[0] = v0 ? g0[r * bxg + x0] : 0.f; av[2] = v0 ? g0[r * bxg + x0 + 4] : 0.f;
+                    av[1] = v1 ? g1[r * bxg + x0] : 0.f; av[3] = v1 ? g1[r * bxg + x0 + 4] : 0.f;
+                    bs0 += av[0] + av[2];
+                    bs1 += av[1] + av[3];
+                    float ah[4], al[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { ah[i] = wg_tf32_hi(av[i]); al[i] = av[i] - ah[i]; }
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky) {
+                        const float* xr = xin + (r + ky) * bxi + x0;
+                        float h0[3], h1[3], l0[3], l1[3];
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) {
+                            const float b0 = vc ? xr[kx] : 0.f, b1 = vc ? xr[kx + 4] : 0.f;
+                            h0[kx] = wg_tf32_hi(b0); h1[kx] = wg_tf32_hi(b1);
+                            l0[kx] = b0 - h0[kx]; l1[kx] = b1 - h1[kx];
+                        }
+                        // (issue order: MMAs on the same accumulator are three slots apart)
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) wg_mma(acc[ky * 3 + kx], ah, h0[kx], h1[kx]);
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) wg_mma(acc[ky * 3 + kx], ah, l0[kx], l1[kx]);
+#pragma unroll
+                        for (int kx = 0; kx < 3; ++kx) wg_mma(acc[ky * 3 + kx], al, h0[kx], h1[kx]);
+                    }
+                }
+                r += dr; seg += ds;
+                if (seg >= nseg) { seg -= nseg; ++r; }
+            }
+            // drain the strip's chains into the register sums (round to nearest)
+#pragma unroll
+            for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { sum[tp][i] += acc[tp][i]; acc[tp][i] = 0.f; }
+        }
+        __syncthreads();                                               // everyone is done with this stage
+        if (tid == 0 && k + kWtStages < n_my) issue(k + kWtStages);
+    }
+    // ---- fold pixel partitions (fixed order) and write this CTA's partial ----
+    __syncthreads();
+    float* sRed = smem;                                                // [P][Oc][Cc][9] | [P][Oc]
+    float* sBias = smem + (size_t)P * Oc * Cc * 9;
+    if (active) {
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int co = mt * 16 + q + ((i & 2) ? 8 : 0), ci = nt * 8 + 2 * t + (i & 1);
+                if (co < Oc && ci < Cc) sRed[(((size_t)part * Oc + co) * Cc + ci) * 9 + tp] = sum[tp][i];
+            }
+        bs0 += __shfl_xor_sync(0xffffffffu, bs0, 1); bs0 += __shfl_xor_sync(0xffffffffu, bs0, 2);
+        bs1 += __shfl_xor_sync(0xffffffffu, bs1, 1); bs1 += __shfl_xor_sync(0xffffffffu, bs1, 2);
+        if (nt == 0 && t == 0) {
+            if (v0) sBias[part * Oc + co0] = bs0;
+            if (v1) sBias[part * Oc + co1] = bs1;
+        }
+    }
+    __syncthreads();
+    const int nW = a.Cout * a.Cin * 9;
+    float* out = a.partials + (size_t)blockIdx.x * (nW + a.Cout);
+    const int blockW = Oc * Cc * 9;
+    for (int e = tid; e < blockW + (c_base == 0 ? Oc : 0); e += kWtThreads) {
+        float s = 0.f;
+        if (e < blockW) {
+            for (int p = 0; p < P; ++p) s += sRed[(size_t)p * blockW + e];
+            const int co = e / (Cc * 9), ci = (e / 9) % Cc, tp = e % 9;
+            out[((size_t)(o_base + co) * a.Cin + c_base + ci) * 9 + tp] = s;
+        } else {
+            const int co = e - blockW;
+            for (int p = 0; p < P; ++p) s += sBias[p * Oc + co];
+            out[nW + o_base + co] = s;
+        }
+    }
+}
+#endif   // !PAIG_EMU
+
 // ---- host ---------------------------------------------------------------------------------------------------
 namespace {
 
@@ -289,6 +461,14 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
     const size_t budget = (110 * 1024 - 128) / sizeof(float);
     const int COB = (a.Cout % 8) == 0 ? 8 : 4;
     if (a.Cout % COB) return -1;
+#ifdef PAIG_EMU
+    const bool mma = false;
+#else
+    static const bool mma_off = getenv("PAIG_NO_WGRAD_MMA") != nullptr || getenv("PAIG_NO_MMA") != nullptr;
+    // tensor-core variant: rows are whole 8-pixel segments; m-tiles of 16 output channels (with 8, half of every MMA is
+    // padding and the FMA kernel wins: 24->8@32 0.187 vs 0.109 ms, 8->8@32 0.128 vs 0.094, profiles/r2o_wgrad_layers.txt)
+    const bool mma = !mma_off && (S % 8) == 0 && (a.Cout % 16) == 0;
+#endif
     const int cands[7] = {(S + 1) | 1, 13, 11, 9, 7, 5, 3};
     bool found = false;
     WgradTmaArgs best = a;
@@ -301,6 +481,7 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
             if (a.Cin % csets || a.Cout % osets) continue;
             const int Cc = a.Cin / csets, Oc = a.Cout / osets;
             if (Oc % COB || (Oc / COB) * Cc > kWtThreads || Cc > 256 || Oc > 256) continue;
+            if (mma && ((Oc + 15) / 16) * ((Cc + 7) / 8) > kWtThreads / 32) continue;    // one (m-tile, n-tile) pair per warp
             double best_cost = 0;
             for (int ci = 0; ci < 7; ++ci) {
                 const int R = forced_R > 0 ? forced_R : cands[ci];
@@ -331,7 +512,11 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
     const int sets = a.csets * (a.Cout / a.Oc);
     const int G_per = (a.Oc / COB) * a.Cc;
     const int P = kWtThreads / G_per > 0 ? kWtThreads / G_per : 1;
-    const size_t red = (size_t)P * G_per * COB * 10;
+    size_t red = (size_t)P * G_per * COB * 10;
+    if (mma) {
+        const int Pm = (kWtThreads / 32) / (((a.Oc + 15) / 16) * ((a.Cc + 7) / 8));
+        red = (size_t)Pm * a.Oc * (a.Cc * 9 + 1);
+    }
     const size_t tile = (size_t)a.stages * a.stage_floats;
     const size_t smem = (tile > red ? tile : red) * sizeof(float) + 128;
     if (smem > 110 * 1024) return -1;
@@ -345,6 +530,10 @@ int conv3x3_wgrad_tma(const WgradArgs& w, float* dW, float* db, cudaStream_t st)
         fprintf(stderr, "[paig] wgrad_tma %d->%d S=%d N=%d R=%d strips=%d stages=%d in box %dx%d g box %dx%d stage=%d floats smem=%zu ctas=%d blocks=%dx%d (Cc=%d Oc=%d)\n",
                 a.Cin, a.Cout, S, a.N, a.R, a.strips, a.stages, a.vin.boxx, a.vin.boxy, a.vg.boxx, a.vg.boxy, a.stage_floats, smem, ctas,
                 a.csets, sets / a.csets, a.Cc, a.Oc);
+#ifndef PAIG_EMU
+    if (mma) launch(conv3x3_wgrad_mma_kernel, dim3(ctas, sets), dim3(kWtThreads), smem, st, a);
+    else
+#endif
     if (COB == 8) launch(conv3x3_wgrad_tma_kernel<8>, dim3(ctas, sets), dim3(kWtThreads), smem, st, a);
     else launch(conv3x3_wgrad_tma_kernel<4>, dim3(ctas, sets), dim3(kWtThreads), smem, st, a);
     int rc = check_launch(layer_name("conv3x3_wgrad", -a.Cin, a.Cout, a.S));   // (negative Cin marks the TMA kernel)
