@@ -6,6 +6,8 @@
 //             -> rollout^T -> velocity^T -> encoder^T -> templates^T
 #include "common.cuh"
 #include "internal.h"
+
+#include <mutex>
 #include "layout.h"
 
 #include <cstring>
@@ -157,8 +159,8 @@ int step_backward(const paig_task* t, const paig_params* p, const paig_params* g
     const Layout L = make_layout(t, B);
     const Dims& d = L.d;
     const size_t seq_fl = (size_t)B * (d.steps + 1) * 4 * d.n, ep_fl = (size_t)L.N * 2 * d.n;
-    cudaMemsetAsync(ws + L.d_seq, 0, seq_fl * sizeof(float), st);
-    cudaMemsetAsync(ws + L.d_enc_pos, 0, ep_fl * sizeof(float), st);
+    if (cudaMemsetAsync(ws + L.d_seq, 0, seq_fl * sizeof(float), st) != cudaSuccess) return check_launch("memset");
+    if (cudaMemsetAsync(ws + L.d_enc_pos, 0, ep_fl * sizeof(float), st) != cudaSuccess) return check_launch("memset");
     DecSeg A, R, none;
     segments(t, L, ws, x, &A, &R);
     route_dloc(L, ws, &A, &R);
@@ -175,7 +177,7 @@ int step_backward(const paig_task* t, const paig_params* p, const paig_params* g
                              ws + L.d_consts, 0, st)))
             return rc;
     } else {
-        cudaMemsetAsync(ws + L.d_consts, 0, CN * sizeof(float), st);
+        if (cudaMemsetAsync(ws + L.d_consts, 0, CN * sizeof(float), st) != cudaSuccess) return check_launch("memset");
     }
     if (d_enc_pos) {
         launch(axpy_kernel, dim3(cdiv(ep_fl, 256)), dim3(256), 0, st, ws + L.d_enc_pos, d_enc_pos, (long)ep_fl);
@@ -276,16 +278,40 @@ int paig_step_fused_host(const paig_task* t, const paig_params* p, const paig_pa
     const Layout L = make_layout(t, B);
     float* ws = (float*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemcpyAsync(ws + L.x_stage, x_host, (size_t)B * L.d.T * L.d.CHW * sizeof(float), cudaMemcpyHostToDevice, st);
+    if (cudaMemcpyAsync(ws + L.x_stage, x_host, (size_t)B * L.d.T * L.d.CHW * sizeof(float), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return check_launch("step_fused_host: input copy");
     int rc = step_fused(t, p, grads, ws + L.x_stage, B, nullptr, ws, st);
     if (rc) return rc;
-    cudaMemcpyAsync(losses_host, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (cudaMemcpyAsync(losses_host, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return check_launch("step_fused_host: losses copy");
     return check_launch("step_fused_host");
 }
 
 // ---- pipelined host input: copy batch k+1 on a side stream while step k computes -----------------------------------
+// One event per (workspace, slot): two workspaces / devices / nets in one process never share a staging event.
 #ifndef PAIG_EMU
-static cudaEvent_t g_stage_ev[2] = {nullptr, nullptr};
+namespace {
+struct StageEvents { const void* ws; cudaEvent_t ev[2]; };
+constexpr int kMaxStagedWorkspaces = 64;
+StageEvents g_stage[kMaxStagedWorkspaces];
+int g_stage_n = 0;
+std::mutex g_stage_mu;
+// create = false: look up only (nullptr when the slot was never staged on this workspace)
+cudaEvent_t stage_event(const void* ws, int slot, bool create) {
+    std::lock_guard<std::mutex> lock(g_stage_mu);
+    int k = 0;
+    for (; k < g_stage_n; ++k)
+        if (g_stage[k].ws == ws) break;
+    if (k == g_stage_n) {
+        if (!create || g_stage_n == kMaxStagedWorkspaces) return nullptr;
+        g_stage[k] = StageEvents{ws, {nullptr, nullptr}};
+        ++g_stage_n;
+    }
+    if (!g_stage[k].ev[slot] && create && cudaEventCreateWithFlags(&g_stage[k].ev[slot], cudaEventDisableTiming) != cudaSuccess)
+        return nullptr;
+    return g_stage[k].ev[slot];
+}
+}  // namespace
 #endif
 
 int paig_stage_input_host(const paig_task* t, const float* x_host, int B, int slot, void* workspace, void* copy_stream) {
@@ -294,11 +320,13 @@ int paig_stage_input_host(const paig_task* t, const float* x_host, int B, int sl
     const Layout L = make_layout(t, B);
     float* ws = (float*)workspace;
     cudaStream_t cs = (cudaStream_t)copy_stream;
-    cudaMemcpyAsync(ws + (slot ? L.x_stage2 : L.x_stage), x_host, (size_t)B * L.d.T * L.d.CHW * sizeof(float),
-                    cudaMemcpyHostToDevice, cs);
+    if (cudaMemcpyAsync(ws + (slot ? L.x_stage2 : L.x_stage), x_host, (size_t)B * L.d.T * L.d.CHW * sizeof(float),
+                        cudaMemcpyHostToDevice, cs) != cudaSuccess)
+        return check_launch("stage_input_host: copy");
 #ifndef PAIG_EMU
-    if (!g_stage_ev[slot]) cudaEventCreateWithFlags(&g_stage_ev[slot], cudaEventDisableTiming);
-    cudaEventRecord(g_stage_ev[slot], cs);
+    cudaEvent_t ev = stage_event(workspace, slot, true);
+    if (!ev) { set_error("stage_input_host: no staging event (more than %d workspaces staged?)", kMaxStagedWorkspaces); return 1; }
+    if (cudaEventRecord(ev, cs) != cudaSuccess) return check_launch("stage_input_host: event");
 #endif
     return check_launch("stage_input_host");
 }
@@ -311,12 +339,14 @@ int paig_step_fused_staged(const paig_task* t, const paig_params* p, const paig_
     float* ws = (float*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
 #ifndef PAIG_EMU
-    if (!g_stage_ev[slot]) { set_error("step_fused_staged: slot %d was never staged", slot); return 1; }
-    cudaStreamWaitEvent(st, g_stage_ev[slot], 0);
+    cudaEvent_t ev = stage_event(workspace, slot, false);
+    if (!ev) { set_error("step_fused_staged: slot %d of this workspace was never staged", slot); return 1; }
+    if (cudaStreamWaitEvent(st, ev, 0) != cudaSuccess) return check_launch("step_fused_staged: wait");
 #endif
     int rc = step_fused(t, p, grads, ws + (slot ? L.x_stage2 : L.x_stage), B, nullptr, ws, st);
     if (rc) return rc;
-    if (losses_host) cudaMemcpyAsync(losses_host, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (losses_host && cudaMemcpyAsync(losses_host, ws + L.losses, 4 * sizeof(float), cudaMemcpyDeviceToHost, st) != cudaSuccess)
+        return check_launch("step_fused_staged: losses copy");
     return check_launch("step_fused_staged");
 }
 
@@ -367,7 +397,7 @@ int paig_velocity_backward(const paig_task* t, const paig_params* p, const paig_
     float* ws = (float*)workspace;
     cudaStream_t st = (cudaStream_t)stream;
     // d_state0 = [0 | d_vel]
-    cudaMemsetAsync(ws + L.d_state0, 0, (size_t)B * 4 * d.n * sizeof(float), st);
+    if (cudaMemsetAsync(ws + L.d_state0, 0, (size_t)B * 4 * d.n * sizeof(float), st) != cudaSuccess) return check_launch("memset");
     cudaMemcpy2DAsync(ws + L.d_state0 + 2 * d.n, 4 * d.n * sizeof(float), d_vel, 2 * d.n * sizeof(float),
                       2 * d.n * sizeof(float), B, cudaMemcpyDeviceToDevice, st);
     return velocity_backward(t, p, grads, L, ws + L.d_state0, d_enc_pos_accum, ws, st);
