@@ -162,11 +162,12 @@ def test_tcgen05_gemm_tf32x3_vs_fp64(M, N, K, fixed):
         # the point of the drained kernel: no coherent shrink.  Same-sign operands make a truncating accumulator's
         # bias visible as a mean signed relative error (one accumulation chain per split: about -2e-6)
         Ap, Bp = A.abs() + 0.05, B.abs() + 0.01
-        _lib.check(lib.paig_debug_gemm_tc(Ap.data_ptr(), Bp.data_ptr(), C.data_ptr(), M, N, K, 2, scratch.data_ptr(),
+        Cp = torch.empty_like(C)
+        _lib.check(lib.paig_debug_gemm_tc(Ap.data_ptr(), Bp.data_ptr(), Cp.data_ptr(), M, N, K, 2, scratch.data_ptr(),
                                           scratch.numel(), st), "gemm_tc")
         torch.cuda.synchronize()
         refp = Ap.double() @ Bp.double().t()
-        bias = ((C.double() - refp) / refp).mean().item()
+        bias = ((Cp.double() - refp) / refp).mean().item()
         assert abs(bias) < 6e-8, bias
     # the same product again: bit-identical (fixed summation order)
     C2 = torch.empty_like(C)
