@@ -96,11 +96,11 @@ __device__ __forceinline__ void ct_mma(unsigned tmem_d, uint64_t da, uint64_t db
         ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
         : "memory");
 }
-__device__ __forceinline__ float ct_tf32(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// x rounded to TF32 (nearest, ties away from zero: what cvt.rna.tf32.f32 computes for finite values).  That instruction is
+// emulated on sm_100a (FSETP + SEL + LOP3 + IADD); the converter warps are what bounds these kernels, and on the bit
+// pattern the rounding is one add and one mask.  (The lo part is rounded the same way: left to the tensor core's own
+// truncation of the low 13 bits, the 64-px task lost its thin parity margin at B = 100, profiles/r2q_cheap_split.txt.)
+__device__ __forceinline__ float ct_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void ct_split4(const float4 x, float4& h, float4& l) {
     h.x = ct_tf32(x.x); l.x = ct_tf32(x.x - h.x);
     h.y = ct_tf32(x.y); l.y = ct_tf32(x.y - h.y);

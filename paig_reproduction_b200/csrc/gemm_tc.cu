@@ -74,11 +74,11 @@ __device__ __forceinline__ void umma_tf32(unsigned tmem_d, uint64_t da, uint64_t
         : "memory");
 }
 // round to nearest TF32 (10-bit mantissa); the result is an fp32 value with the low 13 mantissa bits clear
-__device__ __forceinline__ float tf32_rn(float x) {
-    unsigned r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
-}
+// x rounded to TF32 (nearest, ties away from zero: what cvt.rna.tf32.f32 computes for finite values).  That instruction is
+// emulated on sm_100a (FSETP + SEL + LOP3 + IADD); the converter warps are what bounds these kernels, and on the bit
+// pattern the rounding is one add and one mask.  (The lo part is rounded the same way: left to the tensor core's own
+// truncation of the low 13 bits, the 64-px task lost its thin parity margin at B = 100, profiles/r2q_cheap_split.txt.)
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void umma_commit(unsigned long long* b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(b)) : "memory");
 }

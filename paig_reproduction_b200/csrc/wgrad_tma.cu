@@ -235,8 +235,11 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_tma_kernel(const 
 // convolutions, whose error is amplified by the network behind them, drain every MMA).  The g fragment of an 8-pixel
 // segment is split once and reused by 27 MMAs; per MMA the loop issues ~3 other instructions, against ~8 tensor-pipe
 // cycles: the kernel is bound by the tensor pipe (512 MAC/clk/SM, 170 after the split) where the FMA loop reached 47.
-// Pairs (m-tile, n-tile) x pixel partitions (rows r = part, part + P, ...) are dealt to the 8 warps; the host picks
-// channel blocks with at most 8 pairs.
+// Pairs (m-tile, n-tile) x pixel partitions (units = (row, 8-pixel segment), dealt round-robin) go to the 8 warps; the host
+// picks channel blocks with at most 8 pairs.  Measured and not adopted (profiles/r2o_*): one accumulator set per product type
+// without the drain (108 accumulators: spills, 2x slower) and a (pair, tap row) item per warp with two units in flight
+// (12 + 24 accumulators, same-register MMAs six slots apart, but the g fragment split three times and 6 of 8 warps busy:
+// 16->16@32 0.155 ms against 0.123).
 __device__ __forceinline__ float wg_tf32_hi(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ void wg_mma(float (&d)[4], const float (&a)[4], float b0, float b1) {
     asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -261,19 +264,11 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_mma_kernel(const 
     const int co0 = mt * 16 + q, co1 = co0 + 8, cil = nt * 8 + q;                 // local to the channel block
     const bool v0 = co0 < Oc, v1 = co1 < Oc, vc = cil < Cc;
 
-#ifdef PAIG_WG_EXPERIMENT
-    float acc[9][4], sum[9][4], accC[9][4], bs0 = 0.f, bs1 = 0.f;       // speed experiment: one accumulator per product type, no drain
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) acc[tp][i] = sum[tp][i] = accC[tp][i] = 0.f;
-#else
     float acc[9][4], sum[9][4], bs0 = 0.f, bs1 = 0.f;
 #pragma unroll
     for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[tp][i] = sum[tp][i] = 0.f;
-#endif
     const int items = a.N * a.strips;
     const int n_my = blockIdx.x < items ? (items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const unsigned stage_bytes = (unsigned)((Cc * a.in_plane + Oc * a.g_plane) * sizeof(float));
@@ -344,29 +339,20 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_mma_kernel(const 
                         // (issue order: MMAs on the same accumulator are three slots apart)
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) wg_mma(acc[ky * 3 + kx], ah, h0[kx], h1[kx]);
-#ifdef PAIG_WG_EXPERIMENT
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) wg_mma(sum[ky * 3 + kx], ah, l0[kx], l1[kx]);
-#pragma unroll
-                        for (int kx = 0; kx < 3; ++kx) wg_mma(accC[ky * 3 + kx], al, h0[kx], h1[kx]);
-#else
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) wg_mma(acc[ky * 3 + kx], ah, l0[kx], l1[kx]);
 #pragma unroll
                         for (int kx = 0; kx < 3; ++kx) wg_mma(acc[ky * 3 + kx], al, h0[kx], h1[kx]);
-#endif
                     }
                 }
                 r += dr; seg += ds;
                 if (seg >= nseg) { seg -= nseg; ++r; }
             }
-#ifndef PAIG_WG_EXPERIMENT
             // drain the strip's chains into the register sums (round to nearest)
 #pragma unroll
             for (int tp = 0; tp < 9; ++tp)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) { sum[tp][i] += acc[tp][i]; acc[tp][i] = 0.f; }
-#endif
         }
         __syncthreads();                                               // everyone is done with this stage
         if (tid == 0 && k + kWtStages < n_my) issue(k + kWtStages);
@@ -375,12 +361,6 @@ __global__ void __launch_bounds__(kWtThreads, 2) conv3x3_wgrad_mma_kernel(const 
     __syncthreads();
     float* sRed = smem;                                                // [P][Oc][Cc][9] | [P][Oc]
     float* sBias = smem + (size_t)P * Oc * Cc * 9;
-#ifdef PAIG_WG_EXPERIMENT
-#pragma unroll
-    for (int tp = 0; tp < 9; ++tp)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sum[tp][i] += acc[tp][i] + accC[tp][i];
-#endif
     if (active) {
 #pragma unroll
         for (int tp = 0; tp < 9; ++tp)
