@@ -355,7 +355,7 @@ def main():
         f_fwd = sum(2.0 * 9 * ci * co * s * s for ci, co, s in convs) * N
         f_dgrad = sum(2.0 * 9 * ci * co * s * s for ci, co, s in convs[1:]) * N       # no input gradient for c1
         # fused kernels (unet_fused.cu) or, under PAIG_UNET_LAYERWISE=1, the per-layer conv3x3 kernel
-        flops = {"unet_fused_fwd": f_fwd, "unet_fused_bwd": f_dgrad, "conv3x3": f_fwd + f_dgrad, "conv3x3_wgrad": f_fwd,
+        flops = {"unet_fused_fwd": f_fwd, "unet_tc_fwd": f_fwd, "unet_fused_bwd": f_dgrad, "conv3x3": f_fwd + f_dgrad, "conv3x3_wgrad": f_fwd,
                  "sgemm": 2.0 * 3 * (2 * N) * (3072 * 200 + 200 * 200 + 200 * 2)}
         # the MLP GEMMs are profiled under several names (sgemm, sgemm_l1_fwd, ...): one group for the roofline
         sg = [k for k in kern if k.startswith("sgemm")]

@@ -200,6 +200,7 @@ Layout make_layout(const paig_task* t, int B) {
         L.convtc = take(mx);
     }
     L.wpack = take(unet_wpack_floats(L.unet, t));
+    L.wpack_tc = take(t->deep_unet ? 0 : unet_tc_wpack_floats(L.unet));
     L.frames = take(acts_on_chip ? 0 : N * d.CHW);
     L.x_stage = take(bwd((size_t)B * d.T * d.CHW));
     L.x_stage2 = take(bwd((size_t)B * d.T * d.CHW));
@@ -668,7 +669,8 @@ int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, c
     // whole UNet in one persistent kernel when a frame's activations fit in shared memory (ShallowUNet); the
     // per-layer interpreter otherwise (64x64 UNet) or when PAIG_UNET_LAYERWISE=1 (A/B measurements)
     static const bool layerwise = getenv("PAIG_UNET_LAYERWISE") != nullptr;
-    int rc = layerwise ? -1 : unet_fused_forward(t, p, L, x, seq_stride, fps, ws, st);
+    int rc = layerwise ? -1 : unet_tc_forward(t, p, L, x, seq_stride, fps, ws, st);        // tcgen05 (32-px frames)
+    if (rc < 0 && !layerwise) rc = unet_fused_forward(t, p, L, x, seq_stride, fps, ws, st);
     if (rc < 0) rc = unet_forward(t, p, L, ws, frames, st);
     if (rc) return rc;
     float* masks = ws + L.masks;

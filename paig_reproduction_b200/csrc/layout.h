@@ -51,6 +51,7 @@ struct Layout {
     size_t tc_scratch;           // transposed operands of the tcgen05 encoder.l1 GEMMs: W1^T | dH1^T | A^T
     size_t convtc;               // packed weights of the layer in flight on the tcgen05 conv path (deep UNet)
     size_t wpack;                // UNet weights re-packed [ci][tap][co]|bias for the fused forward kernel
+    size_t wpack_tc;             // ... and as hi / lo TF32 operand blocks for the tcgen05 forward (unet_tc.cu)
     size_t frames;               // gathered encoder frames [N,3,H,H] (when they are a prefix of each sequence)
     size_t x_stage;              // device copy of the input for the *_host entry points (slot 0)
     size_t x_stage2;             // second slot: paig_stage_input_host(slot 1) lands here while a step reads slot 0
@@ -59,11 +60,67 @@ struct Layout {
 
 Layout make_layout(const paig_task* t, int B);
 
+// Static shared-memory planner: blocks with [born, dies] step intervals are placed largest first at the lowest
+// offset that is free over their whole interval (interval-graph colouring heuristic; near-optimal here).
+struct Planner {
+    struct Blk { int size, born, dies, off; int* dst; };
+    Blk b[96];
+    int n = 0;
+    void add(int size, int born, int dies, int* dst) {
+        b[n++] = Blk{(size + 3) & ~3, born, dies, -1, dst};       // 16-byte granularity
+    }
+    int place(int mode = 0) {                                      // returns the peak (floats)
+        int order[96];
+        for (int i = 0; i < n; ++i) order[i] = i;
+        // mode 0: size descending.  1: lifetime descending, then size.  2: birth ascending, then size descending.
+        auto before = [&](const Blk& x, const Blk& y) {
+            if (mode == 1 && (x.dies - x.born) != (y.dies - y.born)) return (x.dies - x.born) > (y.dies - y.born);
+            if (mode == 2 && x.born != y.born) return x.born < y.born;
+            return x.size > y.size;
+        };
+        for (int i = 1; i < n; ++i)                                // insertion sort
+            for (int j = i; j > 0 && before(b[order[j]], b[order[j - 1]]); --j) {
+                const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
+            }
+        int peak = 0;
+        for (int oi = 0; oi < n; ++oi) {
+            Blk& x = b[order[oi]];
+            int off = 0;
+            for (;;) {
+                bool moved = false;
+                for (int pj = 0; pj < oi; ++pj) {
+                    const Blk& y = b[order[pj]];
+                    if (y.born > x.dies || x.born > y.dies) continue;             // never alive together
+                    if (off < y.off + y.size && y.off < off + x.size) { off = y.off + y.size; moved = true; }
+                }
+                if (!moved) break;
+            }
+            x.off = off;
+            *x.dst = off;
+            if (off + x.size > peak) peak = off + x.size;
+        }
+        return peak;
+    }
+    int place_best() {                                             // the ordering heuristic with the lowest peak
+        int best = 0, best_peak = place(0);
+        for (int m = 1; m < 3; ++m) {
+            const int pk = place(m);
+            if (pk < best_peak) { best_peak = pk; best = m; }
+        }
+        return place(best);
+    }
+};
+
+
 // unet_fused.cu -- whole-UNet forward in one persistent kernel; returns -1 when the network does not fit on chip
 size_t unet_wpack_floats(const UNetDesc& u, const paig_task* t);
 int unet_fused_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride, int fps,
                        float* ws, cudaStream_t st);
 int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st);
+// unet_tc.cu -- the same forward on the tcgen05 tensor cores (3xTF32, taps batched along N); -1: not applicable / switched off
+int unet_tc_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride, int fps,
+                    float* ws, cudaStream_t st);
+size_t unet_tc_wpack_floats(const UNetDesc& u);
 
 // encoder.cu
 int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride,

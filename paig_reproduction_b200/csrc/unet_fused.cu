@@ -1021,43 +1021,7 @@ struct Slice {
     int floats;
 };
 
-// Static shared-memory planner: blocks with [born, dies] step intervals are placed largest first at the lowest
-// offset that is free over their whole interval (interval-graph colouring heuristic; near-optimal here).
-struct Planner {
-    struct Blk { int size, born, dies, off; int* dst; };
-    Blk b[96];
-    int n = 0;
-    void add(int size, int born, int dies, int* dst) {
-        b[n++] = Blk{(size + 3) & ~3, born, dies, -1, dst};       // 16-byte granularity
-    }
-    int place() {                                                  // returns the peak (floats)
-        int order[96];
-        for (int i = 0; i < n; ++i) order[i] = i;
-        for (int i = 1; i < n; ++i)                                // insertion sort, size descending
-            for (int j = i; j > 0 && b[order[j]].size > b[order[j - 1]].size; --j) {
-                const int t = order[j]; order[j] = order[j - 1]; order[j - 1] = t;
-            }
-        int peak = 0;
-        for (int oi = 0; oi < n; ++oi) {
-            Blk& x = b[order[oi]];
-            int off = 0;
-            for (;;) {
-                bool moved = false;
-                for (int pj = 0; pj < oi; ++pj) {
-                    const Blk& y = b[order[pj]];
-                    if (y.born > x.dies || x.born > y.dies) continue;             // never alive together
-                    if (off < y.off + y.size && y.off < off + x.size) { off = y.off + y.size; moved = true; }
-                }
-                if (!moved) break;
-            }
-            x.off = off;
-            *x.dst = off;
-            if (off + x.size > peak) peak = off + x.size;
-        }
-        return peak;
-    }
-};
-
+// (struct Planner: layout.h)
 
 // Thread tile of a conv: CO output channels x PY rows x 4 pixels.  Cost model per input channel, for the busiest
 // SM sub-partition: FMA issue slots vs shared-memory wavefronts (measured: 16-byte pixel load 4, 8-byte 4 (2-way

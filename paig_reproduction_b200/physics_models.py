@@ -214,6 +214,7 @@ class PhysicsNet(BaseNetTorch):
         self._gravity_A0 = 1.0          # exp(log 1) * exp(2 log 1): the constructor-time value (cells.py:91-94)
         self._ws_nograd: Dict[int, torch.Tensor] = {}
         self._ws_pools: Dict[tuple, _Pool] = {}
+        self._last_ws = None
         self._last: Optional[dict] = None
         self._flat_grad: Optional[torch.Tensor] = None
         self.optimizer = None
@@ -299,6 +300,7 @@ class PhysicsNet(BaseNetTorch):
                                          ws.data_ptr(), stream), "paig_step_forward")
         out["_lease"] = lease
         out["_x"] = x
+        self._last_ws = weakref.ref(ws)           # parity tests read the ReLU decisions of this forward back (tests/stage_checks.py)
         return out
 
     def _run_backward(self, inp, ws, d_out, d_rec, d_enc_pos, d_seq):

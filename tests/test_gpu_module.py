@@ -9,6 +9,7 @@ import torch
 
 from oracle import physicsnet_oracle as po
 from oracle.make_golden import CASES, grad_digest
+import stage_checks as sc
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -19,6 +20,49 @@ def _net(task, T, alpha, alt_vel=False):
     spec = po.TASKS[task]
     return PhysicsNet(task, 100, 1, po.CELL_TYPE_NAMES[spec.cell], T, spec.input_steps, spec.pred_steps, alpha, alt_vel,
                       True, spec.H * spec.H, "conv_encoder", "conv_st_decoder", device=DEV)
+
+
+def _our_relu_decisions(net, spec, B, T):
+    """ReLU decisions (activation > 0) of the drop-in's latest training forward, read back from its workspace, in the form the
+    oracle's `force` argument takes (tests/stage_checks.relu_decisions)."""
+    from paig_reproduction_b200 import _lib
+    ws = net._last_ws()
+    assert ws is not None
+    torch.cuda.synchronize()
+
+    class Be:
+        lib = _lib.load()
+
+        @staticmethod
+        def check(rc):
+            assert rc == 0, Be.lib.paig_last_error()
+
+    class Ws:
+        @staticmethod
+        def np():
+            return ws.cpu().numpy()
+    return sc.relu_decisions(Be, net._task(T), spec, B, Ws)
+
+
+def _grads_match(pairs, tol, net, spec, x, recompute):
+    """Every (name, ours, reference) within tol -- or, when a ReLU pre-activation that lies inside fp32 rounding noise was
+    decided differently from the reference (a whole pixel's contribution then moves between the two gradients: with 30
+    frames in the batch one flip in 1.7 M decisions shifts a bias gradient by 1e-3..1e-2), within the SAME tol of the oracle
+    evaluated under our decisions (the criterion of tests/test_gpu_stages.py; the oracle itself is pinned to the reference
+    by tests/test_oracle_golden.py).  The flips must be a vanishing fraction of the decisions."""
+    try:
+        for k, ours, ref in pairs:
+            _close(ours, ref, tol)
+        return
+    except AssertionError:
+        pass
+    B, T = x.shape[0], x.shape[1]
+    force = _our_relu_decisions(net, spec, B, T)
+    flips, total = sc.kink_flips(force, {k: v.detach().cpu() for k, v in net.state_dict().items()}, x.cpu(), spec)
+    assert 0 < flips <= max(2, total // 200000), "flipped ReLU decisions: %d of %d" % (flips, total)
+    ref2 = recompute(force)
+    for k, ours, _ in pairs:
+        _close(ours, ref2[k], tol)
 
 
 def _close(a, b, rtol):
@@ -65,12 +109,12 @@ def test_matches_reference_goldens(golden_dir, case):
     if mode == "train":
         live = sorted(k for k, p in net.named_parameters() if p.grad is not None)
         assert live == gold_grads                                     # same set of live parameters (Q1 / Q6)
-        for k, p in net.named_parameters():
-            if p.grad is not None:
-                # digests (sum, L2 norm, 48 samples) vs the reference's autograd; a ReLU decision that flips within
-                # rounding noise moves single-pixel contributions (tests/stage_checks.py), hence 1e-3 here and the
-                # kink-aligned 1e-4 bound in test_gpu_stages.py
-                _close(grad_digest(p.grad.detach().cpu()), gold["grad/" + k], 1e-1 if gravity else 1e-3)
+        # digests (sum, L2 norm, 48 samples) vs the reference's autograd at 1e-3 (the kink-aligned 1e-4 bound is
+        # test_gpu_stages.py's); see _grads_match for what happens when a ReLU decision flips within rounding noise
+        sd0 = po.init_state_dict(spec, seed, alt_vel)
+        pairs = [(k, grad_digest(p.grad.detach().cpu()), gold["grad/" + k]) for k, p in net.named_parameters() if p.grad is not None]
+        _grads_match(pairs, 1e-1 if gravity else 1e-3, net, spec, x,
+                     lambda force: {k: grad_digest(g) for k, g in po.live_step(sd0, x.cpu(), spec, alpha, alt_vel, force)[2].items()})
     else:
         assert all(p.grad is None for p in net.parameters())
 
@@ -96,12 +140,16 @@ def test_stale_mode_matches_reference_semantics():
     # oracle with the prediction branch detached
     leaves = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k not in ("rollout_cell.dt", "rollout_cell.m"))
               for k, v in sd.items()}
-    ff = po.feedforward(leaves, x, spec)
-    ff["output"] = ff["output"].detach()
-    po.losses(x, ff, spec, alpha)["train"].backward()
-    for k, v in leaves.items():
-        if v.grad is not None and not (k.startswith("velocity_encoder.") or k.startswith("rollout_cell.")):
-            _close(grads[k].cpu().numpy(), v.grad.numpy(), 1e-4)
+    def oracle_grads(force):
+        for v in leaves.values():
+            v.grad = None
+        ff = po.feedforward(leaves, x, spec, False, force)
+        ff["output"] = ff["output"].detach()
+        po.losses(x, ff, spec, alpha)["train"].backward()
+        return {k: v.grad.numpy().copy() for k, v in leaves.items()
+                if v.grad is not None and not (k.startswith("velocity_encoder.") or k.startswith("rollout_cell."))}
+    ref = oracle_grads(None)
+    _grads_match([(k, grads[k].cpu().numpy(), r) for k, r in ref.items()], 1e-4, net, spec, x, oracle_grads)
 
 
 def test_fused_train_step_equals_drop_in_path_and_state_dict_round_trip(tmp_path):
