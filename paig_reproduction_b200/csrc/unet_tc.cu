@@ -21,10 +21,10 @@
 // of ONE K chunk (3 accumulations) get their own TMEM accumulator; the epilogue adds the chunks in registers with
 // round-to-nearest and adds back the expected truncation loss of a 3-deep chain once (conv_tc.cu explains why).
 //
-// Warp roles (288 threads, one CTA per SM, CTA b handles frames b, b + grid, ...): 0-3 converters, 4-7 epilogue (TMEM lane
-// quarter = warp % 4), 8 MMA issuer + TMEM allocation + weight prefetch (one TMA bulk copy per layer, one layer ahead).
-// Max-pool, the 2x bilinear upsample, the frame load and the 1x1 head are elementwise passes of warps 0-7 between the
-// convolutions.  Everything the backward pass reads leaves the SM as fire-and-forget NCHW stores, exactly where
+// Warp roles (416 threads, one CTA per SM, CTA b handles frames b, b + grid, ...): 0-7 epilogue in two groups that take the
+// tiles in turn (TMEM lane quarter = warp % 4), 8-11 stagers (lo operand), 12 MMA issuer + TMEM allocation + weight
+// prefetch (one TMA bulk copy per layer, one layer ahead).  Max-pool, the 2x bilinear upsample, the frame load and the
+// 1x1 head are elementwise passes of warps 0-11 between the convolutions.  Everything the backward pass reads leaves the SM as fire-and-forget NCHW stores, exactly where
 // unet_fused_fwd_kernel puts it.
 #include "common.cuh"
 #include "internal.h"
@@ -51,11 +51,12 @@ size_t unet_tc_wpack_floats(const UNetDesc& u) {
 int unet_tc_forward(const paig_task*, const paig_params*, const Layout&, const float*, long, int, float*, cudaStream_t) { return -1; }
 #else
 
-constexpr int kTcThreads = 288;
-constexpr int kTcWorkers = 256;          // warps 0-7: elementwise passes
+constexpr int kTcThreads = 416;          // 13 warps: 0-7 epilogue (two groups), 8-11 stagers, 12 MMA issuer
+constexpr int kTcWorkers = 384;          // warps 0-11: elementwise passes
+constexpr int kTcMmaWarp = 12;
 constexpr int kTcMaxOps = 20;
 constexpr int kTcMaxChunks = 4;
-constexpr size_t kTcSmemLimit = 227 * 1024 - 1024;
+constexpr size_t kTcSmemLimit = 227 * 1024 - 4096;      // dynamic part; the op table and the barriers are static
 
 enum { T_CONV = 0, T_POOL = 1, T_UP = 2, T_HEAD = 3 };
 
@@ -71,13 +72,13 @@ struct TcOp {
     const float* bias;
     const float* w1;                     // head: [Cout][Cin]
     float* gout; long gout_bs;           // NCHW destination in the workspace (nullable)
+    float comp;                          // conv: expected relative truncation loss of the main accumulation chain (3 nchunks MMAs)
 };
 struct TcPlan {
     int nops, N, fps, H, first_w, x_off;
     long seq_stride;
     const float* x;
     const float* wpack;
-    float comp;
     long long* timing;                   // PAIG_DEBUG: per-CTA cycle stamps after every op of the CTA's last frame
     int dbg_op;                          // PAIG_DEBUG: the conv whose tiles CTA 0 stamps in detail (timing + 160 * 32 ...)
     TcOp ops[kTcMaxOps];
@@ -96,6 +97,11 @@ __device__ __forceinline__ void tc_wait(unsigned long long* b, unsigned parity) 
 }
 __device__ __forceinline__ void tc_arrive(unsigned long long* b) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem(b)) : "memory");
+}
+__device__ __forceinline__ bool tc_elect() {
+    unsigned p;
+    asm volatile("{ .reg .pred q; elect.sync _|q, 0xffffffff; selp.u32 %0, 1, 0, q; }" : "=r"(p));
+    return p != 0;
 }
 __device__ __forceinline__ void tc_commit(unsigned long long* b) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tc_smem(b)) : "memory");
@@ -144,39 +150,28 @@ __device__ __forceinline__ void tc_bulk(unsigned dst, const float* src, unsigned
 
 // rows 0 and S+1 of every channel quad of an activation buffer are the convolution's zero padding
 __device__ __forceinline__ void tc_zero_halo(unsigned char* buf, int quads, int S, int t, int nthr) {
-    const int qs = (S + 2) * S * 16;
+    const int qs = (S + 2) * S * 16, ls = 31 - __clz(S);    // S is a power of two
     for (int e = t; e < quads * 2 * S; e += nthr) {
-        const int px = e % S, r = (e / S) & 1, q = e / (2 * S);
+        const int px = e & (S - 1), r = (e >> ls) & 1, q = e >> (ls + 1);
         *reinterpret_cast<float4*>(buf + q * qs + (r ? (S + 1) * S * 16 : 0) + px * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
-// Worker side of a convolution (warps 0-7).  Group g = warp / 4 owns the tiles whose running index is g (mod 2), their
-// staging slot and their accumulator set: for each of its tiles it (1) writes lo = rn_tf32(x - upper19(x)) of the tile's rows
-// plus one above and below, (2) waits for the MMAs, (3) drains the accumulator: thread = pixel (TMEM lane), the kx shift is the
-// neighbouring lane.  While one group drains tile i the tensor core works on tile i + 1 of the other group.
-#define TC_STAMP(slot) do { if (tm && (tid & 127) == 0) tm[(t * 8 + (slot))] = clock64(); } while (0)
+// Stager side of a convolution (warps 8-11): lo = rn_tf32(x - upper19(x)) of each tile's rows plus one above and one below,
+// into the two-slot ring the MMA issuer reads the lo operand from; also clears the padding rows of the output buffer.
+#define TC_STAMP(slot) do { if (tm && (threadIdx.x & 127) == 0) tm[(t * 8 + (slot))] = clock64(); } while (0)
 template <int NCH>
-__device__ __forceinline__ void tc_conv_tiles(const TcOp& op, unsigned char* sm, unsigned tmem, unsigned it, int ntiles, int f,
-                                              float comp, unsigned long long* lo_full, unsigned long long* lo_empty,
-                                              unsigned long long* acc_full, long long* tm) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int grp = warp >> 2, gt = tid & 127;
+__device__ __forceinline__ void tc_conv_stage(const TcOp& op, unsigned char* sm, unsigned it, int ntiles,
+                                              unsigned long long* lo_full, unsigned long long* lo_empty, long long* tm) {
+    const int gt = threadIdx.x & 127;
     const int S = op.S, R = 128 / S, Rr = R < S ? R : S;
     const int qs = (S + 2) * S * 16;
-    const int cols = (NCH + 1) * op.npad;
     const int slot_bytes = NCH * 2 * op.stage_q;
-    const int q = warp & 3, m = q * 32 + lane;
-    const unsigned lane_base = tmem + ((unsigned)(q * 32) << 16);
-    const int x = m & (S - 1);
-    const bool valid = m < Rr * S;
-    if (op.out >= 0) tc_zero_halo(sm + op.out, op.Cout / 4, S, tid, kTcWorkers);
+    if (op.out >= 0) tc_zero_halo(sm + op.out, op.Cout / 4, S, gt, 128);
     const int per_q = (Rr + 2) * S;                         // float4 items per channel quad of a staged tile
     for (int t = 0; t < ntiles; ++t) {
         const unsigned i = it + t, s = i & 1u, ph = (i >> 1) & 1u;
-        if ((int)s != grp) continue;
         const int y0 = t * R;
-        // ---- stage lo ----
         TC_STAMP(0);
         tc_wait(&lo_empty[s], ph ^ 1u);                                                        // tile i - 2 has been multiplied
         if (op.stage_slots == 1 && t > 0) tc_wait(&lo_empty[s ^ 1u], ((i - 1) >> 1) & 1u);     // one slot: so has tile i - 1
@@ -196,36 +191,57 @@ __device__ __forceinline__ void tc_conv_tiles(const TcOp& op, unsigned char* sm,
         }
         TC_STAMP(2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");      // (our TMEM reads of tile i - 2 precede the MMAs this releases)
         tc_arrive(&lo_full[s]);
         TC_STAMP(3);
-        // ---- drain ----
-        const int y = y0 + m / S;
+    }
+}
+
+// Epilogue side of a convolution (warps 0-7).  Group g = warp / 4 drains the accumulator sets of the tiles whose running index
+// is g (mod 2): thread = pixel (TMEM lane), the kx shift is the neighbouring lane.  While one group drains tile i the tensor
+// core works on tile i + 1 into the other set.
+__device__ __forceinline__ void tc_conv_drain(const TcOp& op, unsigned char* sm, unsigned tmem, unsigned it, int ntiles, int f,
+                                              unsigned long long* acc_full, unsigned long long* acc_empty, long long* tm) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp >> 2;
+    const int S = op.S, R = 128 / S, Rr = R < S ? R : S;
+    const int qs = (S + 2) * S * 16;
+    const int cols = 2 * op.npad;
+    const int q = warp & 3, m = q * 32 + lane;
+    const unsigned lane_base = tmem + ((unsigned)(q * 32) << 16);
+    const int x = m & (S - 1);
+    const bool valid = m < Rr * S;
+    const float comp = op.comp;
+    for (int t = 0; t < ntiles; ++t) {
+        const unsigned i = it + t, s = i & 1u, ph = (i >> 1) & 1u;
+        if ((int)s != grp) continue;
+        const int y = t * R + m / S;
         tc_wait(&acc_full[s], ph);
         TC_STAMP(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned d0 = lane_base + (2 * cols <= 512 ? s * cols : 0u);
+        const unsigned d0 = lane_base + s * cols;
         for (int co0 = 0; co0 < op.Cout; co0 += 8) {
-            float v[3][NCH + 1][8];
+            float v[3][2][8];                               // [kx][main | corr][co]
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                for (int a = 0; a <= NCH; ++a) tc_ld8(d0 + kx * op.Cout + co0 + a * op.npad, v[kx][a]);
+                for (int a = 0; a < 2; ++a) tc_ld8(d0 + kx * op.Cout + co0 + a * op.npad, v[kx][a]);
             tc_ld_wait();
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
-                for (int a = 0; a <= NCH; ++a) tc_ld_pin(v[kx][a]);
+                for (int a = 0; a < 2; ++a) tc_ld_pin(v[kx][a]);
+            if (co0 + 8 >= op.Cout) {                       // everything of this set is in registers: the next tile may overwrite it
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                tc_arrive(&acc_empty[s]);
+            }
             float o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 float sx[3];
 #pragma unroll
                 for (int kx = 0; kx < 3; ++kx) {
-                    float sum = v[kx][0][j];
-#pragma unroll
-                    for (int a = 1; a < NCH; ++a) sum += v[kx][a][j];
-                    sx[kx] = sum + fmaf(sum, comp, v[kx][NCH][j]);
+                    const float sum = v[kx][0][j];
+                    sx[kx] = sum + fmaf(sum, comp, v[kx][1][j]);
                 }
                 float left = __shfl_up_sync(0xffffffffu, sx[0], 1);
                 float right = __shfl_down_sync(0xffffffffu, sx[2], 1);
@@ -254,7 +270,7 @@ __device__ __forceinline__ void tc_conv_tiles(const TcOp& op, unsigned char* sm,
 
 __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid_constant__ TcPlan P) {
     extern __shared__ __align__(1024) unsigned char sm[];
-    __shared__ unsigned long long wbar[2], lo_full[2], lo_empty[2], acc_full[2];
+    __shared__ unsigned long long wbar[2], lo_full[2], lo_empty[2], acc_full[2], acc_empty[2];
     __shared__ unsigned tmem_slot;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -263,10 +279,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
             tc_bar_init(&lo_full[i], 128);
             tc_bar_init(&lo_empty[i], 1);
             tc_bar_init(&acc_full[i], 1);
+            tc_bar_init(&acc_empty[i], 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem(&tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
@@ -275,7 +292,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const unsigned tmem = tmem_slot;
     const unsigned smb = tc_smem(sm);
-    const bool issuer = tid == kTcWorkers;                 // lane 0 of warp 8
+    const bool issuer = tid == kTcMmaWarp * 32;            // lane 0 of the MMA warp
     unsigned it = 0;                                       // conv tiles so far: every role walks the same sequence
     unsigned wph0 = 0, wph1 = 0;                           // (issuer) phases of the two weight barriers
     const int H = P.H, HW = H * H;
@@ -315,65 +332,78 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
                 const int ntiles = S * S >= 128 ? S * S / 128 : 1;
                 const int R = 128 / S;                      // image rows a 128-pixel tile spans (S = 8: 16, half of them beyond the frame)
                 const int qs = (S + 2) * S * 16;            // bytes between channel quads of an activation buffer
-                const int cols = (op.nchunks + 1) * op.npad;
+                const int cols = 2 * op.npad;               // [main | corr] per accumulator set, two sets
                 const int slot_bytes = op.nchunks * 2 * op.stage_q;
-                if (warp == 8) {
-                    // ===== MMA issuer =====
-                    if (lane == 0) {
+                if (warp == kTcMmaWarp) {
+                    // ===== MMA issuer: the whole warp walks the loop (warp-uniform control flow keeps the descriptor arithmetic in
+                    // uniform registers; with a single thread every operand took a register -> uniform-register move and one MMA
+                    // cost ~130 issue cycles), one elected lane issues =====
+                    {
+                        const bool lead = tc_elect();
                         if (op.wbar == 0) { tc_wait(&wbar[0], wph0); wph0 ^= 1u; }
                         else { tc_wait(&wbar[1], wph1); wph1 ^= 1u; }
-                        const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(op.npad >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
-                        const unsigned wblk = 2u * op.npad * 16u;           // one (chunk, ky, hi|lo) operand block
+                        // MMA 1: [main | corr] (+)= hi x [w_hi | w_lo]  (N = 2 npad: one read of the pixel slab feeds both products);
+                        // MMA 2: corr += lo x w_hi  (N = npad: the first npad rows of the same weight block)
+                        const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(2 * op.npad >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+                        const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(op.npad >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+                        const unsigned wblk = 2u * 2u * op.npad * 16u;      // one (chunk, ky) operand block: [quad][hi rows | lo rows][4]
                         for (int t = 0; t < ntiles; ++t) {
                             const unsigned i = it + t, s = i & 1u, ph = (i >> 1) & 1u;
                             const int y0 = t * R;
-                            long long* tm = (P.timing && blockIdx.x == 0 && k == P.dbg_op) ? P.timing + 160 * 32 : nullptr;
+                            long long* tm = (P.timing && blockIdx.x == 0 && k == P.dbg_op && lane == 0) ? P.timing + 160 * 32 : nullptr;
                             if (tm) tm[t * 8 + 6] = clock64();
-                            tc_wait(&lo_full[s], ph);                       // lo tile staged; accumulator set s drained (same warps, program order)
+                            tc_wait(&lo_full[s], ph);                       // lo tile staged
+                            tc_wait(&acc_empty[s], ph ^ 1u);                // accumulator set s drained (tile i - 2)
                             if (tm) tm[t * 8 + 7] = clock64();
+                            if (tm) tm[256 + t * 4 + 0] = clock64();
                             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                            const unsigned d0 = tmem + (2 * cols <= 512 ? s * cols : 0u);
-                            const unsigned d_corr = d0 + op.nchunks * op.npad;
+                            const unsigned d0 = tmem + s * cols;
                             const unsigned stg = smb + op.stage + (op.stage_slots == 2 ? s * slot_bytes : 0u);
                             // descriptors differ only in their start-address field (bits 0-13, units of 16 bytes): one full
-                            // encoding per operand kind, then additions (the issue rate of this one thread paces the layer)
+                            // encoding per operand kind, then additions
                             const uint64_t row = (uint64_t)(S * 16 >> 4), wstep = (uint64_t)(wblk >> 4);
-                            uint64_t bh = tc_desc(smb + op.w, op.npad * 16u, 128u);
+                            uint64_t bw = tc_desc(smb + op.w, 2u * op.npad * 16u, 128u);
                             const uint64_t al0 = tc_desc(stg, op.stage_q, 128u);
+                            // (issuing all the hi MMAs first and the lo MMAs after them was measured: 5 % slower)
                             for (int kc = 0; kc < op.nchunks; ++kc) {
                                 uint64_t ah = tc_desc(smb + op.src[kc] + y0 * S * 16, qs, 128u);
                                 uint64_t al = al0 + (uint64_t)((2 * kc * op.stage_q) >> 4);
 #pragma unroll
                                 for (int dy = 0; dy < 3; ++dy) {
-                                    tc_mma(d0 + kc * op.npad, ah, bh, idesc, dy > 0 ? 1u : 0u);
-                                    tc_mma(d_corr, ah, bh + wstep, idesc, (kc > 0 || dy > 0) ? 1u : 0u);
-                                    tc_mma(d_corr, al, bh, idesc, 1u);
-                                    ah += row; al += row; bh += 2 * wstep;
+                                    if (lead) tc_mma(d0, ah, bw, idesc1, (kc > 0 || dy > 0) ? 1u : 0u);
+                                    if (lead) tc_mma(d0 + op.npad, al, bw, idesc2, 1u);
+                                    ah += row; al += row; bw += wstep;
                                 }
                             }
-                            tc_commit(&lo_empty[s]);
-                            tc_commit(&acc_full[s]);
+                            if (tm) tm[256 + t * 4 + 1] = clock64();
+                            if (lead) tc_commit(&lo_empty[s]);
+                            if (tm) tm[256 + t * 4 + 2] = clock64();
+                            if (lead) tc_commit(&acc_full[s]);
+                            if (tm) tm[256 + t * 4 + 3] = clock64();
                         }
                     }
                     __syncwarp();
                 } else {
                     long long* tm = (P.timing && blockIdx.x == 0 && k == P.dbg_op) ? P.timing + 160 * 32 : nullptr;
-                    // ===== two groups of four warps, one tile each in turn: stage the tile's lo operand, then drain its accumulator =====
-                    switch (op.nchunks) {
-                        case 1: tc_conv_tiles<1>(op, sm, tmem, it, ntiles, f, P.comp, lo_full, lo_empty, acc_full, tm); break;
-                        case 2: tc_conv_tiles<2>(op, sm, tmem, it, ntiles, f, P.comp, lo_full, lo_empty, acc_full, tm); break;
-                        case 3: tc_conv_tiles<3>(op, sm, tmem, it, ntiles, f, P.comp, lo_full, lo_empty, acc_full, tm); break;
-                        default: tc_conv_tiles<4>(op, sm, tmem, it, ntiles, f, P.comp, lo_full, lo_empty, acc_full, tm);
+                    if (warp < 8) tc_conv_drain(op, sm, tmem, it, ntiles, f, acc_full, acc_empty, tm);
+                    else switch (op.nchunks) {
+                        case 1: tc_conv_stage<1>(op, sm, it, ntiles, lo_full, lo_empty, tm); break;
+                        case 2: tc_conv_stage<2>(op, sm, it, ntiles, lo_full, lo_empty, tm); break;
+                        case 3: tc_conv_stage<3>(op, sm, it, ntiles, lo_full, lo_empty, tm); break;
+                        default: tc_conv_stage<4>(op, sm, it, ntiles, lo_full, lo_empty, tm);
                     }
                 }
                 it += ntiles;
             } else if (tid < kTcWorkers) {
+                long long* tm = (P.timing && blockIdx.x == 0 && k == P.dbg_op && tid == 0) ? P.timing + 160 * 32 : nullptr;
+                if (tm) tm[0] = clock64();
                 const int ls = 31 - __clz(S);                               // S is a power of two: divisions become shifts
                 if (op.kind == T_POOL) {
                     // 2x2 max-pool: S = output side
                     const int Si = 2 * S, quads = op.Cin / 4;
                     const int qsi = (Si + 2) * Si * 16, qso = (S + 2) * S * 16;
                     if (op.out >= 0) tc_zero_halo(sm + op.out, quads, S, tid, kTcWorkers);
+                    if (tm) tm[1] = clock64();
                     for (int e = tid; e < quads * S * S; e += kTcWorkers) {
                         const int x = e & (S - 1), y = (e >> ls) & (S - 1), q = e >> (2 * ls);
                         const unsigned char* p = sm + op.src[0] + q * qsi + ((2 * y + 1) * Si + 2 * x) * 16;
@@ -392,14 +422,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
                     }
                 } else if (op.kind == T_UP) {
                     // 2x bilinear upsample, align_corners = False (the arithmetic of conv.cu's upsample2_kernel: W pass, then H).
-                    // A thread keeps its pixel and walks the channel quads (taps and weights computed once).
                     const int Si = S / 2, quads = op.Cin / 4;
                     const int qsi = (Si + 2) * Si * 16, qso = (S + 2) * S * 16;
                     if (op.out >= 0) tc_zero_halo(sm + op.out, quads, S, tid, kTcWorkers);
                     const int npx = S * S;
-                    const int sub = npx >= kTcWorkers ? 1 : kTcWorkers / npx;      // threads sharing a pixel (16 px: 1, 32 px: 1 with 4 passes)
-                    for (int e = tid % (npx < kTcWorkers ? npx : kTcWorkers) + 0; e < npx; e += kTcWorkers) {
-                        const int x = e & (S - 1), y = e >> ls;
+                    if (tm) tm[1] = clock64();
+                    for (int e = tid; e < quads * npx; e += kTcWorkers) {
+                        const int x = e & (S - 1), y = (e >> ls) & (S - 1), q = e >> (2 * ls);
                         const int ky = y >> 1, kx = x >> 1;
                         int ya, yb, xa, xb;
                         float wya, wyb, wxa, wxb;
@@ -407,23 +436,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
                         else { ya = max(ky - 1, 0); yb = ky; wya = 0.25f; wyb = 0.75f; }
                         if (x & 1) { xa = kx; xb = min(kx + 1, Si - 1); wxa = 0.75f; wxb = 0.25f; }
                         else { xa = max(kx - 1, 0); xb = kx; wxa = 0.25f; wxb = 0.75f; }
-                        const int oaa = ((ya + 1) * Si + xa) * 16, oab = ((ya + 1) * Si + xb) * 16;
-                        const int oba = ((yb + 1) * Si + xa) * 16, obb = ((yb + 1) * Si + xb) * 16;
-                        const int od = ((y + 1) * S + x) * 16;
-                        for (int q = (npx < kTcWorkers ? tid / npx : 0); q < quads; q += sub) {
-                            const unsigned char* src = sm + op.src[0] + q * qsi;
-                            const float4 aa = *reinterpret_cast<const float4*>(src + oaa), ab = *reinterpret_cast<const float4*>(src + oab);
-                            const float4 ba = *reinterpret_cast<const float4*>(src + oba), bb = *reinterpret_cast<const float4*>(src + obb);
-                            float4 o;
-                            o.x = wya * (wxa * aa.x + wxb * ab.x) + wyb * (wxa * ba.x + wxb * bb.x);
-                            o.y = wya * (wxa * aa.y + wxb * ab.y) + wyb * (wxa * ba.y + wxb * bb.y);
-                            o.z = wya * (wxa * aa.z + wxb * ab.z) + wyb * (wxa * ba.z + wxb * bb.z);
-                            o.w = wya * (wxa * aa.w + wxb * ab.w) + wyb * (wxa * ba.w + wxb * bb.w);
-                            if (op.out >= 0) *reinterpret_cast<float4*>(sm + op.out + q * qso + od) = o;
-                            if (op.gout) {
-                                float* g = op.gout + (long)f * op.gout_bs + ((4 * q) << (2 * ls)) + e;
-                                g[0] = o.x; g[npx] = o.y; g[2 * npx] = o.z; g[3 * npx] = o.w;
-                            }
+                        const unsigned char* src = sm + op.src[0] + q * qsi;
+                        const float4 aa = *reinterpret_cast<const float4*>(src + ((ya + 1) * Si + xa) * 16);
+                        const float4 ab = *reinterpret_cast<const float4*>(src + ((ya + 1) * Si + xb) * 16);
+                        const float4 ba = *reinterpret_cast<const float4*>(src + ((yb + 1) * Si + xa) * 16);
+                        const float4 bb = *reinterpret_cast<const float4*>(src + ((yb + 1) * Si + xb) * 16);
+                        float4 o;
+                        o.x = wya * (wxa * aa.x + wxb * ab.x) + wyb * (wxa * ba.x + wxb * bb.x);
+                        o.y = wya * (wxa * aa.y + wxb * ab.y) + wyb * (wxa * ba.y + wxb * bb.y);
+                        o.z = wya * (wxa * aa.z + wxb * ab.z) + wyb * (wxa * ba.z + wxb * bb.z);
+                        o.w = wya * (wxa * aa.w + wxb * ab.w) + wyb * (wxa * ba.w + wxb * bb.w);
+                        if (op.out >= 0) *reinterpret_cast<float4*>(sm + op.out + q * qso + ((y + 1) * S + x) * 16) = o;
+                        if (op.gout) {
+                            float* g = op.gout + (long)f * op.gout_bs + ((4 * q) << (2 * ls)) + (y << ls) + x;
+                            g[0] = o.x; g[npx] = o.y; g[2 * npx] = o.z; g[3 * npx] = o.w;
                         }
                     }
                 } else {
@@ -452,14 +478,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
                     }
                 }
             }
+            if (P.timing && blockIdx.x == 0 && k == P.dbg_op && tid == 0 && op.kind != T_CONV) P.timing[160 * 32 + 2] = clock64();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (P.timing && blockIdx.x == 0 && k == P.dbg_op && tid == 0 && op.kind != T_CONV) P.timing[160 * 32 + 3] = clock64();
             __syncthreads();
+            if (P.timing && blockIdx.x == 0 && k == P.dbg_op && tid == 0 && op.kind != T_CONV) P.timing[160 * 32 + 4] = clock64();
             if (P.timing && tid == 0) P.timing[(long)blockIdx.x * 32 + 1 + k] = clock64();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 8) {
+    if (warp == kTcMmaWarp) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u));
     }
@@ -471,7 +500,8 @@ struct TcPack {
     int Cin[16], Cout[16], nchunks[16], npad[16];
     long off[16];
 };
-// dst[layer][kc][ky][v][quad][n][j] = split_v(W[co][ci = 8 kc + 4 quad + j][ky][kx]),  n = kx Cout + co  (zero beyond Cin / 3 Cout)
+// dst[layer][kc][ky][quad][v][n][j] = split_v(W[co][ci = 8 kc + 4 quad + j][ky][kx]),  n = kx Cout + co  (zero beyond Cin / 3 Cout):
+// per (chunk, ky) one operand block of 2 npad rows, the hi rows first, then the lo rows
 __global__ void __launch_bounds__(256) unet_tc_pack_kernel(const TcPack K, float* __restrict__ dst) {
     const int l = blockIdx.y;
     const int Cin = K.Cin[l], Cout = K.Cout[l], npad = K.npad[l];
@@ -481,11 +511,11 @@ __global__ void __launch_bounds__(256) unet_tc_pack_kernel(const TcPack K, float
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
         const int j = e & 3;
         int r = e >> 2;
-        const int n = r % npad; r /= npad;
+        const int n2 = r % (2 * npad); r /= 2 * npad;
         const int quad = r & 1; r >>= 1;
-        const int v = r & 1; r >>= 1;
         const int ky = r % 3;
         const int kc = r / 3;
+        const int v = n2 >= npad, n = n2 - v * npad;
         const int ci = kc * 8 + quad * 4 + j, kx = n / Cout, co = n - kx * Cout;
         float val = 0.f;
         if (ci < Cin && n < 3 * Cout) val = w[((size_t)co * Cin + ci) * 9 + ky * 3 + kx];
@@ -493,6 +523,20 @@ __global__ void __launch_bounds__(256) unet_tc_pack_kernel(const TcPack K, float
         const float lo = val - hi;
         d[e] = v ? __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xffffe000u) : hi;
     }
+}
+
+// Expected relative truncation loss (in units of 2^-23) of a main accumulator after `chain` MMAs: the tensor core adds the
+// 8 products of an MMA and the fp32 accumulator with truncation.  Calibrated on the mean signed error of every layer's
+// pre-activations against float64 (tools/unet_tc_check.py); PAIG_UNET_TC_KAPPA="k3,k6,k9,k12" overrides.
+static float tc_kappa(int chain) {
+    static float k[4] = {0.27f, 0.65f, 1.14f, 1.63f};
+    static bool init = false;
+    if (!init) {
+        init = true;
+        if (const char* e = getenv("PAIG_UNET_TC_KAPPA")) sscanf(e, "%f,%f,%f,%f", &k[0], &k[1], &k[2], &k[3]);
+    }
+    const int i = chain / 3 - 1;
+    return k[i < 0 ? 0 : (i > 3 ? 3 : i)];
 }
 
 static int tc_sm_count() {
@@ -565,8 +609,8 @@ int unet_tc_forward(const paig_task* t, const paig_params* p, const Layout& L, c
                 if (Sout != 32 && Sout != 16 && Sout != 8) return -1;
                 o.nchunks = cin / 8;
                 o.npad = tc_pad16(3 * o.Cout);
-                if ((o.nchunks + 1) * o.npad > 512) return -1;
-                if (Sout * Sout > 128 && 2 * (o.nchunks + 1) * o.npad > 512) return -1;     // several tiles need two accumulator sets
+                if (4 * o.npad > 512) return -1;                     // two accumulator sets of [main | corr]
+                o.comp = tc_kappa(3 * o.nchunks) * 1.1920929e-7f;
                 o.wbytes = o.nchunks * 3 * 2 * 2 * o.npad * 16;
                 o.wglob = woff;
                 o.bias = p->conv[op.layer].b;
@@ -677,20 +721,18 @@ int unet_tc_forward(const paig_task* t, const paig_params* p, const Layout& L, c
     P.N = L.N; P.fps = fps; P.H = d.H; P.seq_stride = seq_stride; P.x = x;
     float* wpack = ws + L.wpack_tc;
     P.wpack = wpack;
-    static const float kappa = getenv("PAIG_UNET_TC_KAPPA") ? (float)atof(getenv("PAIG_UNET_TC_KAPPA")) : 0.27f;
-    P.comp = kappa * 1.1920929e-7f;
     launch(unet_tc_pack_kernel, dim3(4, K.nlayers), dim3(256), 0, st, K, wpack);
     int rc = check_launch("pack_weights");
     if (rc) return rc;
     const int grid = L.N < tc_sm_count() ? L.N : tc_sm_count();
     static long long* tbuf = nullptr;
-    if (debug && !tbuf) cudaMalloc(&tbuf, (size_t)162 * 32 * sizeof(long long));
+    if (debug && !tbuf) cudaMalloc(&tbuf, (size_t)172 * 32 * sizeof(long long));
     P.dbg_op = getenv("PAIG_UNET_TC_DBGOP") ? atoi(getenv("PAIG_UNET_TC_DBGOP")) : 0;
     P.timing = debug ? tbuf : nullptr;
     launch(unet_tc_fwd_kernel, dim3(grid), dim3(kTcThreads), (size_t)((peak + 1023) & ~(size_t)1023), st, P);
     rc = check_launch("unet_tc_fwd");
     if (debug && !rc && grid <= 160) {
-        static long long host[162 * 32];
+        static long long host[172 * 32];
         cudaStreamSynchronize(st);
         cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost);
         fprintf(stderr, "[paig] tcgen05 UNet forward cycles per op (last frame of each CTA, mean over %d CTAs):", grid);
@@ -707,6 +749,8 @@ int unet_tc_forward(const paig_task* t, const paig_params* p, const Layout& L, c
         for (int t2 = 0; t2 < 8; ++t2) {
             fprintf(stderr, "[paig]    tile %d:", t2);
             for (int j = 0; j < 8; ++j) fprintf(stderr, " %lld", tm[t2 * 8 + j] ? tm[t2 * 8 + j] - tm[0] : -1);
+            fprintf(stderr, " | waits done, mmas issued, commit 1, commit 2:");
+            for (int j = 0; j < 4; ++j) fprintf(stderr, " %lld", tm[256 + t2 * 4 + j] ? tm[256 + t2 * 4 + j] - tm[0] : -1);
             fprintf(stderr, "\n");
         }
     }
