@@ -2,30 +2,38 @@
 // resident in shared memory (as in unet_fused.cu), every 3x3 convolution a handful of tcgen05.mma instructions.
 //
 // Why a second formulation.  As an implicit GEMM with one MMA per tap (conv_tc.cu: M = 128 pixels, N = Cout, K = 8 input
-// channels) a layer with 8..32 output channels is bound by the 4 KB pixel slab every MMA reads from shared memory, whatever N
-// is: at N = 16 the tensor path only ties with the FMA loop.  Here the taps of a row are batched along N:
+// channels) a layer with 8..32 output channels is bound by the pixel slab every MMA reads from shared memory, whatever N is
+// (measured here: a tf32 MMA with M = 128 costs ~80-130 cycles from shared memory for any N <= 192, i.e. the operand-A fetch
+// of 128 rows paces it): at N = 16 the tensor path only ties with the FMA loop.  Here the taps of a row
+// AND the two halves of the weight split are batched along N:
 //
-//      D[pixel p, (kx, co)] = sum_{ky, ci} in[p + (ky - 1) rows, ci] * w[co, ci, ky, kx]        M = 128, N = 3 Cout, K = 3 Cin
+//      D[pixel p, (kx, co)] = sum_{ky, ci} in[p + (ky - 1) rows, ci] * w[co, ci, ky, kx]        M = 128, K = 3 Cin
 //      out[y, x, co]        = D[(y, x-1), 0, co] + D[(y, x), 1, co] + D[(y, x+1), 2, co] + b[co]
 //
 // The ky shift is a START ADDRESS (activations live as [channel quad][row][pixel][4 channels], a pixel row shift is S x 16
 // bytes: the K-major "no swizzle" core-matrix layout, 8 pixels x 16 bytes contiguous); the kx shift is left to the epilogue,
 // where pixel x-1 / x+1 of the same image row is the neighbouring lane of the warp that drains the accumulator: two shuffles
 // and two additions per output instead of 9 Cin FMAs.  Every pixel slab is read 3 times per K chunk instead of 9 and
-// multiplies 3x as many columns.  No halo columns, no im2col, no per-tap conversion.
+// multiplies 6x as many columns.  No halo columns, no im2col, no per-tap conversion.
 //
 // fp32 accuracy (3xTF32): the tensor core reads the upper 19 bits of an fp32 operand, so the resident fp32 plane IS the hi
-// operand (hi = x with the low 13 mantissa bits dropped); the converter warps write lo = rn_tf32(x - hi) (exact difference,
+// operand (hi = x with the low 13 mantissa bits dropped); the stager warps write lo = rn_tf32(x - hi) (exact difference,
 // rounded to nearest) for the 4..16 rows of the tile in flight into a small staging ring -- the frame is not stored twice.
-// Weights are split once per step (hi = rn_tf32(w), lo = rn_tf32(w - hi)).  a.b ~ hi.hi + hi.lo + lo.hi.  The hi.hi products
-// of ONE K chunk (3 accumulations) get their own TMEM accumulator; the epilogue adds the chunks in registers with
-// round-to-nearest and adds back the expected truncation loss of a 3-deep chain once (conv_tc.cu explains why).
+// Weights are split once per step (hi = rn_tf32(w), lo = rn_tf32(w - hi)) and packed per (K chunk, ky) as ONE operand block
+// [w_hi rows | w_lo rows], so that per (tile, K chunk, ky) two MMAs do the three products:
+//      [main | corr] (+)= hi x [w_hi | w_lo]      (N = 2 npad)          corr += lo x w_hi      (N = npad, same block)
+// The epilogue adds main + corr in fp32 (round to nearest) together with the expected truncation loss of the main chain
+// (the tensor core accumulates with truncation; 3 Cin/8 MMAs per chain; kappa per chain length calibrated against float64,
+// tc_kappa() below -- the same device conv_tc.cu uses, which explains why a coherent 1e-7 bias matters here).
 //
-// Warp roles (416 threads, one CTA per SM, CTA b handles frames b, b + grid, ...): 0-7 epilogue in two groups that take the
-// tiles in turn (TMEM lane quarter = warp % 4), 8-11 stagers (lo operand), 12 MMA issuer + TMEM allocation + weight
-// prefetch (one TMA bulk copy per layer, one layer ahead).  Max-pool, the 2x bilinear upsample, the frame load and the
-// 1x1 head are elementwise passes of warps 0-11 between the convolutions.  Everything the backward pass reads leaves the SM as fire-and-forget NCHW stores, exactly where
-// unet_fused_fwd_kernel puts it.
+// Warp roles (448 threads, one CTA per SM, CTA b handles frames b, b + grid, ...): 0-7 epilogue in two groups that take the
+// tiles in turn (TMEM lane quarter = warp % 4), 8-11 stagers (lo operand), 12-13 MMA issuers (even / odd tiles; warp 12 also
+// allocates TMEM and prefetches the weights: one TMA bulk copy per layer, one layer ahead).  Max-pool, the 2x bilinear
+// upsample, the frame load and the 1x1 head are elementwise passes of warps 0-11 between the convolutions.  Everything the
+// backward pass reads leaves the SM as fire-and-forget NCHW stores, exactly where unet_fused_fwd_kernel puts it.
+//
+// Measured (B200, 1000 frames of 32 x 32, profiles/r2s_*): 0.49 ms against 0.72 ms for the FMA kernel; closer to float64
+// than the FMA kernel on every layer (tools/unet_tc_check.py).  PAIG_UNET_TC=0 selects the FMA kernel.
 #include "common.cuh"
 #include "internal.h"
 #include "layout.h"
@@ -51,7 +59,7 @@ size_t unet_tc_wpack_floats(const UNetDesc& u) {
 int unet_tc_forward(const paig_task*, const paig_params*, const Layout&, const float*, long, int, float*, cudaStream_t) { return -1; }
 #else
 
-constexpr int kTcThreads = 416;          // 13 warps: 0-7 epilogue (two groups), 8-11 stagers, 12 MMA issuer
+constexpr int kTcThreads = 448;          // 14 warps: 0-7 epilogue (two groups), 8-11 stagers, 12-13 MMA issuers (even / odd tiles)
 constexpr int kTcWorkers = 384;          // warps 0-11: elementwise passes
 constexpr int kTcMmaWarp = 12;
 constexpr int kTcMaxOps = 20;
@@ -334,8 +342,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
                 const int qs = (S + 2) * S * 16;            // bytes between channel quads of an activation buffer
                 const int cols = 2 * op.npad;               // [main | corr] per accumulator set, two sets
                 const int slot_bytes = op.nchunks * 2 * op.stage_q;
-                if (warp == kTcMmaWarp) {
-                    // ===== MMA issuer: the whole warp walks the loop (warp-uniform control flow keeps the descriptor arithmetic in
+                if (warp >= kTcMmaWarp) {
+                    // ===== MMA issuers (warp 12: even tiles, warp 13: odd tiles -- one warp's barrier round trips hide under the
+                    // other's MMAs): the whole warp walks the loop (warp-uniform control flow keeps the descriptor arithmetic in
                     // uniform registers; with a single thread every operand took a register -> uniform-register move and one MMA
                     // cost ~130 issue cycles), one elected lane issues =====
                     {
@@ -349,6 +358,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
                         const unsigned wblk = 2u * 2u * op.npad * 16u;      // one (chunk, ky) operand block: [quad][hi rows | lo rows][4]
                         for (int t = 0; t < ntiles; ++t) {
                             const unsigned i = it + t, s = i & 1u, ph = (i >> 1) & 1u;
+                            if ((int)s != warp - kTcMmaWarp) continue;
                             const int y0 = t * R;
                             long long* tm = (P.timing && blockIdx.x == 0 && k == P.dbg_op && lane == 0) ? P.timing + 160 * 32 : nullptr;
                             if (tm) tm[t * 8 + 6] = clock64();
@@ -529,7 +539,7 @@ __global__ void __launch_bounds__(256) unet_tc_pack_kernel(const TcPack K, float
 // 8 products of an MMA and the fp32 accumulator with truncation.  Calibrated on the mean signed error of every layer's
 // pre-activations against float64 (tools/unet_tc_check.py); PAIG_UNET_TC_KAPPA="k3,k6,k9,k12" overrides.
 static float tc_kappa(int chain) {
-    static float k[4] = {0.27f, 0.65f, 1.14f, 1.63f};
+    static float k[4] = {0.27f, 0.70f, 1.225f, 1.75f};
     static bool init = false;
     if (!init) {
         init = true;

@@ -1,4 +1,4 @@
-"""profiles/r2_ncu_traffic.json from ONE capture set (profiles/run_ncu_r2.sh): DRAM bytes read + written per launch of
+"""profiles/r2_ncu_traffic.json from ONE capture set (profiles/run_ncu_r2s.sh): DRAM bytes read + written per launch of
 the kernels bench.py's roofline can name, taken from the `ncu --set full` raw exports in gpurun_out/.
 
     python profiles/make_traffic_json.py gpurun_out/r2_fused_fwd_raw.csv gpurun_out/r2_fused_bwd_raw.csv ... > profiles/r2_ncu_traffic.json
@@ -9,7 +9,7 @@ import csv
 import json
 import sys
 
-PER_STEP = {"unet_fused_fwd": 1, "unet_fused_bwd": 1, "conv3x3_wgrad": 12}
+PER_STEP = {"unet_tc_fwd": 1, "unet_fused_fwd": 1, "unet_fused_bwd": 1, "conv3x3_wgrad": 12}
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 out, seen = {}, {}
 for path in sys.argv[1:]:
@@ -27,5 +27,5 @@ for path in sys.argv[1:]:
         out[key] = out.get(key, 0.0) + tot
         seen[key] = seen.get(key, 0) + 1
 res = {k: (out[k] if seen.get(k) == n else None) for k, n in PER_STEP.items() if k in out}
-res["_source"] = "profiles/run_ncu_r2.sh: " + ", ".join("%s x%d" % (k, v) for k, v in seen.items())
+res["_source"] = "profiles/run_ncu_r2s.sh: " + ", ".join("%s x%d" % (k, v) for k, v in seen.items())
 print(json.dumps(res, indent=1))

@@ -1,6 +1,9 @@
 """Parity of each C-ABI stage of libpaig_b200.so on a B200 against the oracle / reference goldens."""
+import numpy as np
 import pytest
+import torch
 
+from oracle import physicsnet_oracle as po
 import stage_checks as sc
 
 pytestmark = pytest.mark.gpu
@@ -175,3 +178,92 @@ def test_tcgen05_gemm_tf32x3_vs_fp64(M, N, K, fixed):
                                       scratch.numel(), st), "gemm_tc")
     torch.cuda.synchronize()
     assert torch.equal(C, C2)
+
+
+def _encoder_activations(be, task, B, seed, tc):
+    """Every saved UNet activation + the encoder outputs of paig_step_forward, with the ShallowUNet forward on tcgen05
+    (csrc/unet_tc.cu) or on the FMA kernel (csrc/unet_fused.cu).  PAIG_UNET_TC is read per call."""
+    import ctypes
+    import os
+    from paig_reproduction_b200 import _abi
+    spec = po.TASKS[task]
+    T = spec.seq_len
+    sd = po.init_state_dict(spec, seed, False)
+    x = po.synthetic_frames(spec, B, T, seed)
+    n, H, e, steps = spec.n_objs, spec.H, spec.enc_steps, T - spec.input_steps
+    tk = be.make_task(spec, T, 3.0, False, 0)
+    bufs = be.sd(sd)
+    P = be.make_params(spec, bufs, False)
+    xd = be.dev(x.numpy())
+    ws = be.workspace(tk, B)
+    ob = dict(output_seq=be.zeros((B, steps, 3, H, H)), recons_out=be.zeros((B, e, 3, H, H)), enc_pos=be.zeros((B, e, 2 * n)),
+              pos_vel_seq=be.zeros((B, steps + 1, 4 * n)), enc_masks=be.zeros((B * e, n + 1, H, H)),
+              masked_objs=be.zeros((n, B * e, 3, H, H)), templates=be.zeros(n * (H // 2) ** 2 * 4 + 3 * H * H), losses=be.zeros(4))
+    O = _abi.Outputs(*[ob[k].ptr for k in ("output_seq", "recons_out", "enc_pos", "pos_vel_seq", "enc_masks", "masked_objs",
+                                           "templates", "losses")])
+    prev = os.environ.get("PAIG_UNET_TC")
+    os.environ["PAIG_UNET_TC"] = "1" if tc else "0"
+    try:
+        be.lib.paig_profile_begin()
+        be.check(be.lib.paig_step_forward(ctypes.byref(tk), ctypes.byref(P), xd.ptr, B, ctypes.byref(O), ws.ptr, be.stream))
+        buf = ctypes.create_string_buffer(1 << 16)
+        be.lib.paig_profile_end(buf, len(buf))
+    finally:
+        if prev is None:
+            os.environ.pop("PAIG_UNET_TC", None)
+        else:
+            os.environ["PAIG_UNET_TC"] = prev
+    w = ws.np()
+    acts = {}
+    N = B * e
+    for layer in range(13):
+        view = (ctypes.c_long * 5)()
+        be.check(be.lib.paig_debug_unet_conv_view(ctypes.byref(tk), B, layer, ctypes.byref(view)))
+        off, bs, C, S, relu = [int(v) for v in view]
+        acts["c%d" % (layer + 1)] = (np.stack([w[off + f * bs: off + f * bs + C * S * S] for f in range(N)]).reshape(N, C, S, S), relu)
+    return acts, {k: v.np() for k, v in ob.items()}, buf.value.decode(), sd, x, spec
+
+
+@pytest.mark.parametrize("task,B,seed", [("spring_color", 1, 0), ("spring_color", 17, 3), ("bouncing_balls", 31, 1)])
+def test_tcgen05_unet_forward_vs_fma_kernel_and_float64(be, task, B, seed):
+    """csrc/unet_tc.cu (3xTF32 on tcgen05, row taps batched along N) is the ShallowUNet forward of the 32-px tasks.  Against the
+    FMA kernel on the same input: every saved activation (what the backward pass and the weight gradients read), the logits
+    and the encoder outputs agree to fp32 rounding; against the float64 oracle it is no further away than the FMA kernel, and
+    its pre-activations carry no coherent bias (the tensor core accumulates with truncation: compensated, tc_kappa())."""
+    a0, o0, prof0, sd, x, spec = _encoder_activations(be, task, B, seed, tc=False)
+    a1, o1, prof1, _, _, _ = _encoder_activations(be, task, B, seed, tc=True)
+    assert "unet_tc_fwd" in prof1 and "unet_fused_fwd" not in prof1, prof1          # the tensor-core kernel is what ran
+    assert "unet_fused_fwd" in prof0 and "unet_tc_fwd" not in prof0, prof0
+    for k in a0:
+        assert sc.rel(a1[k][0], a0[k][0]) < 2e-5, k
+    for k in ("enc_pos", "enc_masks", "output_seq", "recons_out"):
+        assert sc.rel(o1[k], o0[k]) < 2e-5, k
+    # float64 yardstick: the oracle's post-ReLU activations (layers with a ReLU)
+    rec = {}
+    orig = po._relu
+
+    def spy(y, f, name):
+        out = orig(y, f, name)
+        rec[name] = out.detach()
+        return out
+    torch.set_default_dtype(torch.float64)
+    po._relu = spy
+    try:
+        with torch.no_grad():
+            sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+            po.encoder(sd64, x[:, :spec.enc_steps].reshape(-1, 3, spec.H, spec.H).double(), spec)
+    finally:
+        po._relu = orig
+        torch.set_default_dtype(torch.float32)
+    checked = 0
+    for name, ref in rec.items():
+        if name not in a0 or not a0[name][1]:
+            continue
+        ref = ref.numpy()
+        e_tc, e_fma = sc.rel(a1[name][0], ref), sc.rel(a0[name][0], ref)
+        assert e_tc < 2e-6 and e_tc < 1.5 * e_fma + 2e-7, (name, e_tc, e_fma)
+        big = ref > 1e-3 * np.abs(ref).max()
+        bias = float(np.mean((a1[name][0][big] - ref[big]) / ref[big]))
+        assert abs(bias) < (2e-6 if name == "c13" else 8e-7), (name, bias)          # c13: logits, differences of large terms
+        checked += 1
+    assert checked >= 10
