@@ -271,7 +271,8 @@ static int unet_backward(const paig_task* t, const paig_params* p, const paig_pa
     // Data gradients of the whole UNet in one persistent kernel (unet_fused.cu) when it fits on chip: every conv
     // output's ReLU-gated gradient lands in the workspace; what remains per layer is its weight gradient.
     static const bool layerwise = getenv("PAIG_UNET_LAYERWISE") != nullptr;
-    int frc = layerwise ? -1 : unet_fused_backward(t, p, L, ws, st);
+    int frc = layerwise ? -1 : unet_tc_backward(t, p, L, ws, st);            // tcgen05 (32-px frames)
+    if (frc < 0 && !layerwise) frc = unet_fused_backward(t, p, L, ws, st);
     if (frc > 0) return frc;
     if (frc == 0) {
         ReduceBatch folds;                               // one launch folds every layer's per-CTA partials at the end

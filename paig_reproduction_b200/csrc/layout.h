@@ -120,6 +120,7 @@ int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& 
 // unet_tc.cu -- the same forward on the tcgen05 tensor cores (3xTF32, taps batched along N); -1: not applicable / switched off
 int unet_tc_forward(const paig_task* t, const paig_params* p, const Layout& L, const float* x, long seq_stride, int fps,
                     float* ws, cudaStream_t st);
+int unet_tc_backward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st);
 size_t unet_tc_wpack_floats(const UNetDesc& u);
 
 // encoder.cu

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include "layout.h"
+#include "unet_plan.h"
 
 #include <cstdint>
 #include <cstdio>
@@ -28,42 +29,9 @@
 namespace paig {
 
 constexpr int kFusedThreads = 512;
-constexpr int kFusedMaxOps = 24;
-// The weight prefetch (proxy fence + expect_tx + bulk copy, several hundred cycles) is issued by the last warp: ops
-// with fewer than 512 thread tiles leave it idle, so the cost leaves the critical path of warp 0.
+// (FusedOp / FusedPlan / PackPlan: unet_plan.h)
 constexpr int kIssueThread = kFusedThreads - 32;
 constexpr size_t kFusedSmemLimit = 227 * 1024 - 4096;   // dynamic part; the op table and barriers are static
-
-enum { F_CONV = 0, F_POOL = 1, F_HEAD = 2, F_UPT = 3, F_POOLT = 4, F_HEADT = 5 };
-
-struct FusedOp {
-    int kind, S, Cin0, Cin1, Cout, relu;
-    int up;                        // >0: segment 0 is the 2x upsample of a half-resolution buffer, built `up` channels at a time
-    int co_tile;                   // output channels per thread: 4, 8 or 16
-    int py_tile;                   // output rows per thread: 1 or 2 (x 4 pixels)
-    int in0, in1, out, chunk;      // shared-memory offsets (floats); out < 0: result is not read on chip
-    int wsm, wfloats, wbar;        // weights: shared offset, packed floats (incl. bias), mbarrier index
-    int next_w;                    // index of the next op that has weights (prefetched while this op runs), or -1
-    long wglob;                    // offset of this layer in the packed weight buffer
-    float* gout; long gout_bs;     // global destination of the result (kept for backward)
-    float* gup; long gup_bs;       // global destination of the upsampled input
-    // backward-data pass (unet_fused_bwd_kernel): transposed convs reuse F_CONV with bias = 0 and a ReLU mask
-    int bias;                      // weights are followed by a bias vector
-    const float* gmask; long gmask_bs;    // activation whose sign gates the result (ReLU adjoint); F_POOLT: the pooled tensor's source
-    const float* gsrc; long gsrc_bs;      // F_HEADT: upstream gradient of the logits
-    const float* gmask2; long gmask2_bs;  // F_HEADT: the logits (head ReLU), nullable
-    int acc_gout;                         // F_POOLT: the other reader's share was parked in gout (global), not in1
-};
-struct FusedPlan {
-    int nops, N, fps, H, first_w;
-    long seq_stride;
-    int x_off;
-    const float* x;
-    const float* wpack;
-    long long* timing;             // debug (PAIG_DEBUG): per-CTA cycle stamps after every op of the CTA's first frames
-    float kappa;                   // tensor-core variant: expected relative truncation loss of one MMA, added back in the epilogue
-    FusedOp ops[kFusedMaxOps];
-};
 
 struct Geo {
     int S, nqx, P, plane;
@@ -951,19 +919,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) unet_fused_bwd_kernel(const 
 }
 
 // ---- weight packing: [co][ci][tap] -> [ci][tap][co] | bias  (head: [co][ci] | bias kept as is) ----------------
-struct PackPlan {
-    int nlayers;
-    const float* w[24];
-    const float* b[24];
-    int Cout[24], Cin[24], taps[24];
-    int mode[24];      // 0: forward [ci][tap][co] | bias.  1: transposed slice for the backward-data pass:
-                       //    dst[(co*9 + tap)*Cout + c] = W[co][ci0 + c][8 - tap]   (Cin = number of co, no bias)
-    int ci0[24], cin_total[24];
-    long off[24];
-    int frag;          // tensor-core variant: 3x3 layers go out in mma.sync A-fragment order
-                       //    dst[(((kc*9 + tap)*mtiles + mt)*32 + lane)*4 + j] = W[co = 16mt + lane/4 + 8(j&1)][ci = 8kc + lane%4 + 4(j>>1)][tap]
-                       //    (zero beyond Cout / Cin), bias after the last fragment
-};
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackPlan P, float* __restrict__ dst) {
     const int l = blockIdx.y;
     if (l >= P.nlayers) return;
@@ -1359,7 +1314,7 @@ static long wpack_bwd_base(const UNetDesc& u) { return (long)(unet_wpack_floats(
 // instead of on chip -- 8-16 planes less shared memory, which is what lets the 36-px frames of 3bp fit.
 // Returns -2 when the plan needs more shared memory than an SM has.
 static int fused_backward_plan(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st,
-                               bool park_global) {
+                               bool park_global, BwdOps* info = nullptr) {
     const UNetDesc& u = L.unet;
     const Dims& d = L.d;
     FusedPlan P;
@@ -1546,6 +1501,12 @@ static int fused_backward_plan(const paig_task* t, const paig_params* p, const L
     P.kappa = fused_mma_kappa();
     for (int k = 0; k < npr; ++k)
         if (gs[k].parked) return -1;                     // a parked gradient nobody finalised
+    if (info) {                                          // the op list only: unet_tc.cu plans and runs it on the tensor cores
+        info->P = P; info->K = K; info->nslices = npr;
+        for (int k = 0; k < nf; ++k) { info->in0_of[k] = in0_of[k]; info->in1_of[k] = in1_of[k]; info->out_of[k] = out_of[k]; }
+        for (int k = 0; k < npr; ++k) { info->born[k] = gs[k].born; info->last[k] = gs[k].last; info->C[k] = pr[k].C; info->S[k] = side_of(pr[k].buf); }
+        return 0;
+    }
     // thread tiling of the transposed convs
     for (int k = 0; k < nf; ++k)
         if (!mma && P.ops[k].kind == F_CONV && !choose_tile(P.ops[k], false)) return -1;
@@ -1615,6 +1576,12 @@ int unet_fused_backward(const paig_task* t, const paig_params* p, const Layout& 
     int rc = fused_backward_plan(t, p, L, ws, st, false);
     if (rc == -2) rc = fused_backward_plan(t, p, L, ws, st, true);
     return rc == -2 ? -1 : rc;
+}
+
+// The backward-data op list of the network (transposed convs, adjoints, who gates / parks / writes what) without planning
+// shared memory or launching anything: the tensor-core backward (unet_tc.cu) runs the same list in its own layout.
+int unet_backward_ops(const paig_task* t, const paig_params* p, const Layout& L, float* ws, bool park_global, BwdOps* info) {
+    return fused_backward_plan(t, p, L, ws, nullptr, park_global, info);
 }
 
 }  // namespace paig

@@ -37,6 +37,7 @@
 #include "common.cuh"
 #include "internal.h"
 #include "layout.h"
+#include "unet_plan.h"
 
 #include <cstdint>
 #include <cstdio>
@@ -47,26 +48,34 @@ namespace paig {
 
 static inline int tc_pad16(int c) { return (c + 15) & ~15; }
 
-// packed weights of the 3x3 layers: [K chunk][ky][hi | lo][channel quad 2][npad][4]
-size_t unet_tc_wpack_floats(const UNetDesc& u) {
+// packed weights of the 3x3 layers: [K chunk][ky][channel quad 2][hi rows | lo rows: 2 npad][4]; the forward packing first
+// (unet_tc_wpack_fwd_floats), then the transposed slices of the backward-data pass (a concat layer's two parts pad separately)
+static size_t unet_tc_wpack_fwd_floats(const UNetDesc& u) {
     size_t total = 64;
     for (int i = 0; i < u.nops; ++i)
         if (u.ops[i].kind == OP_CONV) total += align64((size_t)((u.ops[i].in.C + 7) / 8) * 3 * 2 * 2 * tc_pad16(3 * u.ops[i].out.C) * 4);
     return total;
 }
+size_t unet_tc_wpack_floats(const UNetDesc& u) {
+    size_t total = unet_tc_wpack_fwd_floats(u);
+    for (int i = 0; i < u.nops; ++i)
+        if (u.ops[i].kind == OP_CONV) total += 2 * 64 + (size_t)((u.ops[i].out.C + 7) / 8) * 3 * 2 * 2 * (tc_pad16(3 * u.ops[i].in.C) + 16) * 4;
+    return total;
+}
 
 #ifdef PAIG_EMU
 int unet_tc_forward(const paig_task*, const paig_params*, const Layout&, const float*, long, int, float*, cudaStream_t) { return -1; }
+int unet_tc_backward(const paig_task*, const paig_params*, const Layout&, float*, cudaStream_t) { return -1; }
 #else
 
 constexpr int kTcThreads = 448;          // 14 warps: 0-7 epilogue (two groups), 8-11 stagers, 12-13 MMA issuers (even / odd tiles)
 constexpr int kTcWorkers = 384;          // warps 0-11: elementwise passes
 constexpr int kTcMmaWarp = 12;
-constexpr int kTcMaxOps = 20;
+constexpr int kTcMaxOps = 22;
 constexpr int kTcMaxChunks = 4;
-constexpr size_t kTcSmemLimit = 227 * 1024 - 4096;      // dynamic part; the op table and the barriers are static
+constexpr size_t kTcSmemLimit = 227 * 1024 - 1024;      // dynamic part; the barriers are static
 
-enum { T_CONV = 0, T_POOL = 1, T_UP = 2, T_HEAD = 3 };
+enum { T_CONV = 0, T_POOL = 1, T_UP = 2, T_HEAD = 3, T_HEADT = 4, T_UPT = 5, T_POOLT = 6 };
 
 struct TcOp {
     int kind, S, Cin, Cout, relu;
@@ -81,6 +90,12 @@ struct TcOp {
     const float* w1;                     // head: [Cout][Cin]
     float* gout; long gout_bs;           // NCHW destination in the workspace (nullable)
     float comp;                          // conv: expected relative truncation loss of the main accumulation chain (3 nchunks MMAs)
+    // backward-data pass (the op list of unet_fused.cu's fused_backward_plan, run in this kernel's layout)
+    const float* gmask; long gmask_bs;   // conv / T_UPT / T_HEADT: activation whose sign gates the result; T_POOLT: the pool's source
+    const float* gsrc; long gsrc_bs;     // T_HEADT: d logits
+    const float* gmask2; long gmask2_bs; // T_HEADT: the logits (head ReLU), nullable
+    int in1;                             // T_POOLT: the other reader's share parked on chip (byte offset), -1: none
+    int acc_gout;                        // T_POOLT: ... or parked in gout (global / L2), finalised in place
 };
 struct TcPlan {
     int nops, N, fps, H, first_w, x_off;
@@ -140,6 +155,14 @@ __device__ __forceinline__ void tc_ld8(unsigned taddr, float (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
                  : "r"(taddr));
+}
+// a global load the compiler may not wait for or reorder (volatile): a run of these is in flight together, the first use of a
+// result is where the thread waits.  (Left to the compiler, the gate loads of the backward pass were issued one round trip
+// at a time: 128 registers per thread at 448 threads leave it no room to batch them on its own.)
+__device__ __forceinline__ float tc_ldg_async(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
 }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld_pin(float (&v)[8]) {
@@ -223,6 +246,26 @@ __device__ __forceinline__ void tc_conv_drain(const TcOp& op, unsigned char* sm,
         const unsigned i = it + t, s = i & 1u, ph = (i >> 1) & 1u;
         if ((int)s != grp) continue;
         const int y = t * R + m / S;
+        // ReLU adjoint (backward-data pass): the gates of this pixel's Cout outputs are fetched while the MMAs run and kept as bits
+        unsigned gate_bits = 0xffffffffu;
+        if (op.gmask && valid) {
+            const float* gm = op.gmask + (long)f * op.gmask_bs + y * S + x;
+            gate_bits = 0u;
+            for (int c0 = 0; c0 < op.Cout; c0 += 16) {      // Cout is 8, 16 or 32: 8 or 16 loads in flight
+                float gv[16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) gv[c] = tc_ldg_async(gm + (long)(c0 + c) * S * S);
+                if (op.Cout > 8) {
+#pragma unroll
+                    for (int c = 8; c < 16; ++c) gv[c] = tc_ldg_async(gm + (long)(c0 + c) * S * S);
+                } else {
+#pragma unroll
+                    for (int c = 8; c < 16; ++c) gv[c] = 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 16; ++c) gate_bits |= (gv[c] > 0.f ? 1u : 0u) << (c0 + c);
+            }
+        }
         tc_wait(&acc_full[s], ph);
         TC_STAMP(4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -255,8 +298,9 @@ __device__ __forceinline__ void tc_conv_drain(const TcOp& op, unsigned char* sm,
                 float right = __shfl_down_sync(0xffffffffu, sx[2], 1);
                 if (x == 0) left = 0.f;
                 if (x == S - 1) right = 0.f;
-                float r = (left + sx[1]) + (right + __ldg(op.bias + co0 + j));
+                float r = (left + sx[1]) + (right + (op.bias ? __ldg(op.bias + co0 + j) : 0.f));
                 if (op.relu) r = fmaxf(r, 0.f);
+                if (!((gate_bits >> (co0 + j)) & 1u)) r = 0.f;
                 o[j] = r;
             }
             if (valid) {
@@ -310,7 +354,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
             const TcOp& o = P.ops[P.first_w];
             tc_bulk(smb + o.w, P.wpack + o.wglob, (unsigned)o.wbytes, &wbar[o.wbar]);
         }
-        if (tid < kTcWorkers) {
+        if (tid < kTcWorkers && P.x) {
             // the input frame: quad 0 = (r, g, b, 0), quad 1 = 0 (the first conv's K chunk is 8 channels wide)
             unsigned char* X = sm + P.x_off;
             const int qs = (H + 2) * H * 16;
@@ -462,6 +506,148 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
                             g[0] = o.x; g[npx] = o.y; g[2 * npx] = o.z; g[3 * npx] = o.w;
                         }
                     }
+                } else if (op.kind == T_HEADT) {
+                    // 1x1 head adjoint: d in[c] = sum_o w[o][c] * g[o], g = d logits gated by the head's own ReLU; the result is
+                    // gated by the ReLU of the layer that produced `in`.  Cout = 8 channels of the head's input, Cin = logits.
+                    const int qso = (S + 2) * S * 16, NO = op.Cin;
+                    if (op.out >= 0) tc_zero_halo(sm + op.out, 2, S, tid, kTcWorkers);
+                    float w[3][8];
+#pragma unroll
+                    for (int o = 0; o < 3; ++o)
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) w[o][c] = o < NO ? __ldg(op.w1 + o * 8 + c) : 0.f;
+                    // (a compact loop on purpose: this code runs once per frame, and straight-line code that does not fit the
+                    // instruction cache is paid for line by line -- fully unrolled over its three passes this op took 30 k cycles)
+#pragma unroll 1
+                    for (int e = tid; e < S * S; e += kTcWorkers) {
+                        float gl[3], hm[3], mk[8];
+#pragma unroll
+                        for (int o = 0; o < 3; ++o) {
+                            gl[o] = o < NO ? tc_ldg_async(op.gsrc + (long)f * op.gsrc_bs + (long)o * S * S + e) : 0.f;
+                            hm[o] = (o < NO && op.gmask2) ? tc_ldg_async(op.gmask2 + (long)f * op.gmask2_bs + (long)o * S * S + e) : 1.f;
+                        }
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) mk[c] = op.gmask ? tc_ldg_async(op.gmask + (long)f * op.gmask_bs + (long)c * S * S + e) : 1.f;
+                        float d[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float a = 0.f;
+#pragma unroll
+                            for (int o = 0; o < 3; ++o)
+                                if (o < NO && hm[o] > 0.f) a += w[o][c] * gl[o];
+                            d[c] = mk[c] > 0.f ? a : 0.f;
+                        }
+                        if (op.out >= 0) {
+                            *reinterpret_cast<float4*>(sm + op.out + (S + e) * 16) = make_float4(d[0], d[1], d[2], d[3]);
+                            *reinterpret_cast<float4*>(sm + op.out + qso + (S + e) * 16) = make_float4(d[4], d[5], d[6], d[7]);
+                        }
+                        if (op.gout) {
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) op.gout[(long)f * op.gout_bs + (long)c * S * S + e] = d[c];
+                        }
+                    }
+                } else if (op.kind == T_UPT) {
+                    // upsample adjoint (gather): input (i, j) of a 2x bilinear upsample collects outputs 2i-1..2i+2 x 2j-1..2j+2
+                    // with weights (.25, .75, .75, .25), the clamped border taps folding back (unet_fused.cu run_upT, same
+                    // arithmetic).  S = the low-resolution side; src[0] = the gradient of the upsampled tensor.
+                    const int So = 2 * S, quads = op.Cin / 4;
+                    const int qsi = (So + 2) * So * 16, qso = (S + 2) * S * 16;
+                    if (op.out >= 0) tc_zero_halo(sm + op.out, quads, S, tid, kTcWorkers);
+                    for (int e = tid; e < quads * S * S; e += kTcWorkers) {
+                        const int j = e & (S - 1), i = (e >> ls) & (S - 1), q = e >> (2 * ls);
+                        float wy[4], wx[4];
+                        wy[0] = i > 0 ? 0.25f : 0.f; wy[1] = i > 0 ? 0.75f : 1.f; wy[2] = i < S - 1 ? 0.75f : 1.f; wy[3] = i < S - 1 ? 0.25f : 0.f;
+                        wx[0] = j > 0 ? 0.25f : 0.f; wx[1] = j > 0 ? 0.75f : 1.f; wx[2] = j < S - 1 ? 0.75f : 1.f; wx[3] = j < S - 1 ? 0.25f : 0.f;
+                        float mk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            mk[u] = op.gmask ? tc_ldg_async(op.gmask + (long)f * op.gmask_bs + ((long)(4 * q + u) << (2 * ls)) + (i << ls) + j) : 1.f;
+                        // output (2i-1+a, 2j-1+b): buffer row 2i+a (the padding rows carry weight 0 or zeros), pixel 2j-1+b
+                        const unsigned char* g0 = sm + op.src[0] + q * qsi + (2 * i * So + 2 * j - 1) * 16;
+                        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int a = 0; a < 4; ++a) {
+                            if (wy[a] == 0.f) continue;
+                            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                if (wx[b] == 0.f) continue;
+                                const float4 g = *reinterpret_cast<const float4*>(g0 + (a * So + b) * 16);
+                                r.x += wx[b] * g.x; r.y += wx[b] * g.y; r.z += wx[b] * g.z; r.w += wx[b] * g.w;
+                            }
+                            s4.x += wy[a] * r.x; s4.y += wy[a] * r.y; s4.z += wy[a] * r.z; s4.w += wy[a] * r.w;
+                        }
+                        if (!(mk[0] > 0.f)) s4.x = 0.f;
+                        if (!(mk[1] > 0.f)) s4.y = 0.f;
+                        if (!(mk[2] > 0.f)) s4.z = 0.f;
+                        if (!(mk[3] > 0.f)) s4.w = 0.f;
+                        if (op.out >= 0) *reinterpret_cast<float4*>(sm + op.out + q * qso + ((i + 1) * S + j) * 16) = s4;
+                        if (op.gout) {
+                            float* g = op.gout + (long)f * op.gout_bs + ((long)(4 * q) << (2 * ls)) + (i << ls) + j;
+                            g[0] = s4.x; g[S * S] = s4.y; g[2 * S * S] = s4.z; g[3 * S * S] = s4.w;
+                        }
+                    }
+                } else if (op.kind == T_POOLT) {
+                    // max-pool adjoint: each 2x2 window of the source X routes the pooled gradient to its first maximum (row-major,
+                    // as ATen), adds the gradient that reached X through its other consumer (in1, parked on chip) and applies X's
+                    // own ReLU mask (unet_fused.cu run_poolT).  S = pooled side; gmask = X (global NCHW).
+                    const int Si = 2 * S, quads = op.Cin / 4;
+                    const int qsp = (S + 2) * S * 16, qsx = (Si + 2) * Si * 16;
+                    if (op.out >= 0 && op.out != op.in1) tc_zero_halo(sm + op.out, quads, Si, tid, kTcWorkers);
+                    for (int e = tid; e < quads * S * S; e += kTcWorkers) {
+                        const int x = e & (S - 1), y = (e >> ls) & (S - 1), q = e >> (2 * ls);
+                        float2 xa[4], xb[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float* xs = op.gmask + (long)f * op.gmask_bs + ((long)(4 * q + u) * Si + 2 * y) * Si + 2 * x;
+                            xa[u] = *reinterpret_cast<const float2*>(xs);
+                            xb[u] = *reinterpret_cast<const float2*>(xs + Si);
+                        }
+                        const float4 g4 = *reinterpret_cast<const float4*>(sm + op.src[0] + q * qsp + ((y + 1) * S + x) * 16);
+                        const float g[4] = {g4.x, g4.y, g4.z, g4.w};
+                        const int t00 = q * qsx + ((2 * y + 1) * Si + 2 * x) * 16;
+                        const int toff[4] = {t00, t00 + 16, t00 + Si * 16, t00 + Si * 16 + 16};
+                        float r[4][4];                                              // [window position][channel]
+#pragma unroll
+                        for (int k2 = 0; k2 < 4; ++k2) {
+                            float4 pk = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (op.in1 >= 0) pk = *reinterpret_cast<const float4*>(sm + op.in1 + toff[k2]);
+                            r[k2][0] = pk.x; r[k2][1] = pk.y; r[k2][2] = pk.z; r[k2][3] = pk.w;
+                        }
+                        if (op.acc_gout) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float* ps = op.gout + (long)f * op.gout_bs + ((long)(4 * q + u) * Si + 2 * y) * Si + 2 * x;
+                                const float2 pa = *reinterpret_cast<const float2*>(ps), pb = *reinterpret_cast<const float2*>(ps + Si);
+                                r[0][u] = pa.x; r[1][u] = pa.y; r[2][u] = pb.x; r[3][u] = pb.y;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float v[4] = {xa[u].x, xa[u].y, xb[u].x, xb[u].y};
+                            int best = 0;
+                            float m = v[0];
+                            if (v[1] > m) { m = v[1]; best = 1; }
+                            if (v[2] > m) { m = v[2]; best = 2; }
+                            if (v[3] > m) { m = v[3]; best = 3; }
+#pragma unroll
+                            for (int k2 = 0; k2 < 4; ++k2) {
+                                if (k2 == best) r[k2][u] += g[u];
+                                if (op.relu && !(v[k2] > 0.f)) r[k2][u] = 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int k2 = 0; k2 < 4; ++k2)
+                            if (op.out >= 0) *reinterpret_cast<float4*>(sm + op.out + toff[k2]) = make_float4(r[k2][0], r[k2][1], r[k2][2], r[k2][3]);
+                        if (op.gout) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                float* go = op.gout + (long)f * op.gout_bs + ((long)(4 * q + u) * Si + 2 * y) * Si + 2 * x;
+                                *reinterpret_cast<float2*>(go) = make_float2(r[0][u], r[1][u]);
+                                *reinterpret_cast<float2*>(go + Si) = make_float2(r[2][u], r[3][u]);
+                            }
+                        }
+                    }
                 } else {
                     // 1x1 head: logits[o] = (relu)(b[o] + sum_c w[o][c] * in[c]); Cin <= 8, Cout <= 3 (planner)
                     const int qsi = (S + 2) * S * 16;
@@ -506,9 +692,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
 
 struct TcPack {
     int nlayers;
-    const float* w[16];
-    int Cin[16], Cout[16], nchunks[16], npad[16];
-    long off[16];
+    const float* w[20];
+    int Cin[20], Cout[20], nchunks[20], npad[20];
+    int tr[20], ci0[20], cin_total[20];      // backward-data: W[k][ci0 + n'][2 - ky][2 - kx] of the layer's [Cout_l = K][cin_total][3][3]
+    long off[20];
 };
 // dst[layer][kc][ky][quad][v][n][j] = split_v(W[co][ci = 8 kc + 4 quad + j][ky][kx]),  n = kx Cout + co  (zero beyond Cin / 3 Cout):
 // per (chunk, ky) one operand block of 2 npad rows, the hi rows first, then the lo rows
@@ -528,7 +715,8 @@ __global__ void __launch_bounds__(256) unet_tc_pack_kernel(const TcPack K, float
         const int v = n2 >= npad, n = n2 - v * npad;
         const int ci = kc * 8 + quad * 4 + j, kx = n / Cout, co = n - kx * Cout;
         float val = 0.f;
-        if (ci < Cin && n < 3 * Cout) val = w[((size_t)co * Cin + ci) * 9 + ky * 3 + kx];
+        if (ci < Cin && n < 3 * Cout)
+            val = K.tr[l] ? w[((size_t)ci * K.cin_total[l] + K.ci0[l] + co) * 9 + (2 - ky) * 3 + (2 - kx)] : w[((size_t)co * Cin + ci) * 9 + ky * 3 + kx];
         const float hi = __uint_as_float((__float_as_uint(val) + 0x1000u) & 0xffffe000u);
         const float lo = val - hi;
         d[e] = v ? __uint_as_float((__float_as_uint(lo) + 0x1000u) & 0xffffe000u) : hi;
@@ -558,6 +746,39 @@ static int tc_sm_count() {
         if (n <= 0) n = 148;
     }
     return n;
+}
+
+// PAIG_DEBUG: cycles per op (last frame of every CTA, mean over CTAs) and, for op PAIG_UNET_TC_DBGOP of CTA 0, the stamps of
+// every role inside each tile
+static long long* tc_timing_buffer() {
+    static long long* tbuf = nullptr;
+    if (!tbuf) cudaMalloc(&tbuf, (size_t)172 * 32 * sizeof(long long));
+    return tbuf;
+}
+static void tc_print_timing(const char* what, const TcPlan& P, int grid, cudaStream_t st) {
+    if (grid > 160) return;
+    static long long host[172 * 32];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(host, P.timing, sizeof(host), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[paig] tcgen05 UNet %s cycles per op (last frame of each CTA, mean over %d CTAs):", what, grid);
+    double total = 0;
+    for (int k = 0; k < P.nops; ++k) {
+        double sum = 0;
+        for (int b = 0; b < grid; ++b) sum += (double)(host[b * 32 + 1 + k] - host[b * 32 + k]);
+        fprintf(stderr, " op%d=%.0f", k, sum / grid);
+        total += sum / grid;
+    }
+    fprintf(stderr, " total=%.0f\n", total);
+    if (P.dbg_op < 0) return;
+    const long long* tm = host + 160 * 32;
+    fprintf(stderr, "[paig]   op%d of CTA 0, per tile (cycles since the op's first stamp): start | stage free | staged | arrived | acc full | drained || mma: start | lo full\n", P.dbg_op);
+    for (int t2 = 0; t2 < 8; ++t2) {
+        fprintf(stderr, "[paig]    tile %d:", t2);
+        for (int j = 0; j < 8; ++j) fprintf(stderr, " %lld", tm[t2 * 8 + j] ? tm[t2 * 8 + j] - tm[0] : -1);
+        fprintf(stderr, " | waits done, mmas issued, commit 1, commit 2:");
+        for (int j = 0; j < 4; ++j) fprintf(stderr, " %lld", tm[256 + t2 * 4 + j] ? tm[256 + t2 * 4 + j] - tm[0] : -1);
+        fprintf(stderr, "\n");
+    }
 }
 
 // 0 ok, > 0 error, -1: not applicable (the caller runs unet_fused_forward)
@@ -655,7 +876,7 @@ int unet_tc_forward(const paig_task* t, const paig_params* p, const Layout& L, c
     }
     P.nops = n;
     K.nlayers = nl;
-    if ((size_t)woff > unet_tc_wpack_floats(u)) { set_error("unet_tc: packed weights exceed their workspace region"); return 1; }
+    if ((size_t)woff > unet_tc_wpack_fwd_floats(u)) { set_error("unet_tc: packed weights exceed their workspace region"); return 1; }
     // weight prefetch chain: conv k's weights are fetched while the previous conv runs
     int issue_at[kTcMaxOps];
     {
@@ -735,35 +956,150 @@ int unet_tc_forward(const paig_task* t, const paig_params* p, const Layout& L, c
     int rc = check_launch("pack_weights");
     if (rc) return rc;
     const int grid = L.N < tc_sm_count() ? L.N : tc_sm_count();
-    static long long* tbuf = nullptr;
-    if (debug && !tbuf) cudaMalloc(&tbuf, (size_t)172 * 32 * sizeof(long long));
+    P.timing = debug ? tc_timing_buffer() : nullptr;
     P.dbg_op = getenv("PAIG_UNET_TC_DBGOP") ? atoi(getenv("PAIG_UNET_TC_DBGOP")) : 0;
-    P.timing = debug ? tbuf : nullptr;
     launch(unet_tc_fwd_kernel, dim3(grid), dim3(kTcThreads), (size_t)((peak + 1023) & ~(size_t)1023), st, P);
     rc = check_launch("unet_tc_fwd");
-    if (debug && !rc && grid <= 160) {
-        static long long host[172 * 32];
-        cudaStreamSynchronize(st);
-        cudaMemcpy(host, tbuf, sizeof(host), cudaMemcpyDeviceToHost);
-        fprintf(stderr, "[paig] tcgen05 UNet forward cycles per op (last frame of each CTA, mean over %d CTAs):", grid);
-        double total = 0;
-        for (int k = 0; k < n; ++k) {
-            double sum = 0;
-            for (int b = 0; b < grid; ++b) sum += (double)(host[b * 32 + 1 + k] - host[b * 32 + k]);
-            fprintf(stderr, " op%d=%.0f", k, sum / grid);
-            total += sum / grid;
-        }
-        fprintf(stderr, " total=%.0f\n", total);
-        const long long* tm = host + 160 * 32;
-        fprintf(stderr, "[paig]   op%d of CTA 0, per tile (cycles since the op's first stamp): start | stage free | staged | arrived | acc full | drained || mma: start | lo full\n", P.dbg_op);
-        for (int t2 = 0; t2 < 8; ++t2) {
-            fprintf(stderr, "[paig]    tile %d:", t2);
-            for (int j = 0; j < 8; ++j) fprintf(stderr, " %lld", tm[t2 * 8 + j] ? tm[t2 * 8 + j] - tm[0] : -1);
-            fprintf(stderr, " | waits done, mmas issued, commit 1, commit 2:");
-            for (int j = 0; j < 4; ++j) fprintf(stderr, " %lld", tm[256 + t2 * 4 + j] ? tm[256 + t2 * 4 + j] - tm[0] : -1);
-            fprintf(stderr, "\n");
+    if (debug && !rc) tc_print_timing("forward", P, grid, st);
+    return rc;
+}
+// Backward-data pass of the ShallowUNet on the tensor cores: the op list of unet_fused.cu's planner (transposed convs with the
+// ReLU gate in the epilogue, max-pool / upsample / head adjoints, skip gradients parked on chip) run by the same kernel in
+// its own layout.  0 ok, > 0 error, -1: not applicable (the caller runs unet_fused_backward).
+int unet_tc_backward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st) {
+    const char* sw = getenv("PAIG_UNET_TC_BWD");           // read per call, like PAIG_UNET_TC
+    if (!sw || sw[0] == '0' || getenv("PAIG_NO_TCGEN05")) return -1;
+    const UNetDesc& u = L.unet;
+    const Dims& d = L.d;
+    if (t->deep_unet || d.H != 32) return -1;
+    static BwdOps B;                                       // (large: op table + pack plan)
+    memset(&B, 0, sizeof(B));
+    // skip-connection gradients wait for the max-pool adjoint in the workspace gradient buffer (L2), not on chip: 53 KB less
+    // shared memory, which is what lets every layer keep two staging slots
+    if (unet_backward_ops(t, p, L, ws, true, &B) != 0) return -1;
+    const int n = B.P.nops;
+    if (n > kTcMaxOps) return -1;
+    TcPlan P;
+    memset(&P, 0, sizeof(P));
+    TcPack K;
+    memset(&K, 0, sizeof(K));
+    long woff = (long)unet_tc_wpack_fwd_floats(u);
+    int nl = 0, kw = 0;                                    // kw: index into B.K (ops that have weights, in op order)
+    for (int k = 0; k < n; ++k) {
+        const FusedOp& fo = B.P.ops[k];
+        TcOp& o = P.ops[k];
+        o.out = o.in1 = -1;
+        o.next_w = -1;
+        o.S = fo.S;
+        o.relu = fo.relu;
+        o.gout = fo.gout; o.gout_bs = fo.gout_bs;
+        o.gmask = fo.gmask; o.gmask_bs = fo.gmask_bs;
+        o.acc_gout = fo.acc_gout;
+        switch (fo.kind) {
+            case F_CONV: {
+                o.kind = T_CONV;
+                o.Cin = fo.Cin0; o.Cout = fo.Cout;
+                if (o.Cin % 8 || o.Cin / 8 > kTcMaxChunks || (o.Cout != 8 && o.Cout != 16 && o.Cout != 32)) return -1;
+                o.nchunks = o.Cin / 8;
+                o.npad = tc_pad16(3 * o.Cout);
+                o.comp = tc_kappa(3 * o.nchunks) * 1.1920929e-7f;
+                o.wbytes = o.nchunks * 3 * 2 * 2 * o.npad * 16;
+                o.wglob = woff;
+                if (nl >= 20 || B.K.mode[kw] != 1) return -1;
+                K.w[nl] = B.K.w[kw]; K.Cin[nl] = o.Cin; K.Cout[nl] = o.Cout; K.nchunks[nl] = o.nchunks; K.npad[nl] = o.npad;
+                K.tr[nl] = 1; K.ci0[nl] = B.K.ci0[kw]; K.cin_total[nl] = B.K.cin_total[kw]; K.off[nl] = woff;
+                ++nl; ++kw;
+                woff += (long)align64((size_t)o.wbytes / 4);
+                break;
+            }
+            case F_HEADT:
+                o.kind = T_HEADT;
+                o.Cin = fo.Cin0; o.Cout = fo.Cout;         // logits, channels of the head's input
+                if (o.Cout != 8 || o.Cin > 3 || B.K.mode[kw] != 2) return -1;
+                o.w1 = B.K.w[kw]; ++kw;
+                o.gsrc = fo.gsrc; o.gsrc_bs = fo.gsrc_bs; o.gmask2 = fo.gmask2; o.gmask2_bs = fo.gmask2_bs;
+                break;
+            case F_UPT: o.kind = T_UPT; o.Cin = o.Cout = fo.Cin0; if (o.Cin % 4) return -1; break;
+            case F_POOLT: o.kind = T_POOLT; o.Cin = o.Cout = fo.Cin0; if (o.Cin % 4 || !fo.gmask) return -1; break;
+            default: return -1;
         }
     }
+    P.nops = n;
+    K.nlayers = nl;
+    if ((size_t)woff > unet_tc_wpack_floats(u)) { set_error("unet_tc backward: packed weights exceed their workspace region"); return 1; }
+    int issue_at[kTcMaxOps];
+    {
+        int prev = -1, widx = 0;
+        P.first_w = -1;
+        for (int k = 0; k < n; ++k) {
+            issue_at[k] = -1;
+            if (P.ops[k].kind != T_CONV) continue;
+            P.ops[k].wbar = widx++ & 1;
+            issue_at[k] = prev;
+            if (prev < 0) P.first_w = k; else P.ops[prev].next_w = k;
+            prev = k;
+        }
+    }
+    auto buf_bytes = [](int C, int S) { return (C / 4) * (S + 2) * S * 16 + (S == 8 ? 1024 : 0); };
+    int stage_off[kTcMaxOps], w_off[kTcMaxOps], sl_off[40];
+    size_t peak = 0;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        Planner al;
+        for (int k = 0; k < n; ++k) {
+            TcOp& o = P.ops[k];
+            if (o.kind != T_CONV) continue;
+            o.late_w = attempt >= 1 && o.S == d.H && o.nchunks >= 2;
+            al.add(o.wbytes / 4, o.late_w ? k : issue_at[k], k, &w_off[k]);
+            o.stage_q = (128 / o.S + 2) * o.S * 16;
+            o.stage_slots = (attempt == 3 || (attempt == 2 && o.S == d.H)) ? 1 : 2;
+            al.add(o.stage_slots * o.nchunks * 2 * o.stage_q / 4, k, k, &stage_off[k]);
+        }
+        for (int g = 0; g < B.nslices; ++g) {
+            sl_off[g] = -1;
+            if (B.born[g] < 0 || B.last[g] < 0) continue;
+            al.add(buf_bytes(B.C[g], B.S[g]) / 4, B.born[g], B.last[g], &sl_off[g]);
+        }
+        peak = (size_t)al.place_best() * 4;
+        if (getenv("PAIG_DEBUG")) fprintf(stderr, "[paig] tcgen05 UNet backward: plan attempt %d needs %zu B\n", attempt, peak);
+        if (peak <= kTcSmemLimit) break;
+    }
+    for (int k = 0; k < n; ++k) {
+        TcOp& o = P.ops[k];
+        const int a = B.in0_of[k], b = B.in1_of[k], c = B.out_of[k];
+        if (c >= 0 && B.last[c] >= 0 && sl_off[c] >= 0) o.out = sl_off[c] * 4;
+        if (a >= 0) {
+            if (sl_off[a] < 0) return -1;
+            if (o.kind == T_CONV) {
+                const int qs = (o.S + 2) * o.S * 16;
+                for (int q8 = 0; q8 < o.nchunks; ++q8) o.src[q8] = sl_off[a] * 4 + 2 * q8 * qs;
+            } else o.src[0] = sl_off[a] * 4;
+        } else if (o.kind != T_HEADT) return -1;
+        if (b >= 0) { if (sl_off[b] < 0) return -1; o.in1 = sl_off[b] * 4; }
+        if (o.kind == T_CONV) { o.w = w_off[k] * 4; o.stage = stage_off[k] * 4; }
+    }
+    static const bool debug = getenv("PAIG_DEBUG") != nullptr;
+    if (debug) {
+        fprintf(stderr, "[paig] tcgen05 UNet backward plan: H=%d ops=%d smem=%zu B\n", d.H, n, peak);
+        for (int k = 0; k < n; ++k) {
+            const TcOp& o = P.ops[k];
+            fprintf(stderr, "[paig]   op%-2d kind=%d S=%-2d Cin=%-2d Cout=%-2d relu=%d chunks=%d npad=%d src=%d in1=%d out=%d mask=%d gout=%d stage x%d late=%d\n",
+                    k, o.kind, o.S, o.Cin, o.Cout, o.relu, o.nchunks, o.npad, o.src[0], o.in1, o.out, o.gmask != nullptr, o.gout != nullptr,
+                    o.stage_slots, o.late_w);
+        }
+    }
+    if (peak > kTcSmemLimit) return -1;
+    P.N = L.N; P.fps = 1; P.H = d.H; P.x = nullptr;
+    float* wpack = ws + L.wpack_tc;
+    P.wpack = wpack;
+    launch(unet_tc_pack_kernel, dim3(4, K.nlayers), dim3(256), 0, st, K, wpack);
+    int rc = check_launch("pack_weights");
+    if (rc) return rc;
+    const int grid = L.N < tc_sm_count() ? L.N : tc_sm_count();
+    P.timing = debug ? tc_timing_buffer() : nullptr;
+    P.dbg_op = -1;
+    launch(unet_tc_fwd_kernel, dim3(grid), dim3(kTcThreads), (size_t)((peak + 1023) & ~(size_t)1023), st, P);
+    rc = check_launch("unet_tc_bwd");
+    if (debug && !rc) tc_print_timing("backward-data", P, grid, st);
     return rc;
 }
 #endif
