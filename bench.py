@@ -355,7 +355,7 @@ def main():
         f_fwd = sum(2.0 * 9 * ci * co * s * s for ci, co, s in convs) * N
         f_dgrad = sum(2.0 * 9 * ci * co * s * s for ci, co, s in convs[1:]) * N       # no input gradient for c1
         # fused kernels (unet_fused.cu) or, under PAIG_UNET_LAYERWISE=1, the per-layer conv3x3 kernel
-        flops = {"unet_fused_fwd": f_fwd, "unet_tc_fwd": f_fwd, "unet_fused_bwd": f_dgrad, "conv3x3": f_fwd + f_dgrad, "conv3x3_wgrad": f_fwd,
+        flops = {"unet_fused_fwd": f_fwd, "unet_tc_fwd": f_fwd, "unet_fused_bwd": f_dgrad, "unet_tc_bwd": f_dgrad, "conv3x3": f_fwd + f_dgrad, "conv3x3_wgrad": f_fwd,
                  "sgemm": 2.0 * 3 * (2 * N) * (3072 * 200 + 200 * 200 + 200 * 2)}
         # the MLP GEMMs are profiled under several names (sgemm, sgemm_l1_fwd, ...): one group for the roofline
         sg = [k for k in kern if k.startswith("sgemm")]
@@ -375,10 +375,17 @@ def main():
                 pass
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                     "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic, "peak_source": pk_src + " bf16 sustained",
-                    "note": "fp32 CUDA-core kernel (1e-4 parity excludes single-pass TF32); of the nominal FP32-FMA peak "
-                            "%.1f TFLOP/s it reaches %.3f" % (FP32_FMA_NOMINAL_TFLOPS, ach / FP32_FMA_NOMINAL_TFLOPS),
+                    "note": ("%s; fp32 results (1e-4 gradient parity excludes single-pass TF32: every product is 3 tensor-core "
+                             "products, so the tensor pipe does 3x the algorithmic FLOPs counted here); of the nominal FP32-FMA "
+                             "peak %.1f TFLOP/s the algorithmic rate is %.3f" % (
+                                 {"unet_tc_fwd": "tcgen05 3xTF32 persistent kernel", "unet_tc_bwd": "tcgen05 3xTF32 persistent kernel",
+                                  "conv3x3_wgrad": "12 launches: mma.sync 3xTF32 for layers with 16-channel m-tiles, FP32 FMA for the rest"
+                                  }.get(top, "fp32 CUDA-core kernel"), FP32_FMA_NOMINAL_TFLOPS, ach / FP32_FMA_NOMINAL_TFLOPS)),
                     "share_of_step": kern[top]["ms_per_step"] / kernel_ms if kernel_ms else None,
-                    "algorithmic_flops_per_step": flops[top], "kernel_ms_per_step": kern[top]["ms_per_step"]}
+                    "algorithmic_flops_per_step": flops[top], "kernel_ms_per_step": kern[top]["ms_per_step"],
+                    "unet_kernels_tflops": {k: round(flops[k] / (kern[k]["ms_per_step"] * 1e-3) / 1e12, 1)
+                                            for k in ("unet_tc_fwd", "unet_tc_bwd", "unet_fused_fwd", "unet_fused_bwd", "conv3x3_wgrad")
+                                            if k in kern}}
         line = {"metric": "train sequences/sec (fwd+bwd, spring_color, bs=100)", "value": value, "unit": "sequences/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -354,6 +354,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) unet_tc_fwd_kernel(const __grid
             const TcOp& o = P.ops[P.first_w];
             tc_bulk(smb + o.w, P.wpack + o.wglob, (unsigned)o.wbytes, &wbar[o.wbar]);
         }
+        if (tid < kTcWorkers && !P.x) {
+            // backward-data pass: everything this frame's gates read (saved activations, 350 KB, long evicted from L2 by the
+            // time the backward runs) is requested into L2 now; the head adjoint comes first, so ITS inputs are requested one
+            // frame ahead.  A gate load then costs an L2 round trip instead of a DRAM one.
+            for (int k2 = 0; k2 < P.nops; ++k2) {
+                const TcOp& o = P.ops[k2];
+                const bool head = o.kind == T_HEADT;
+                const int ff = head ? f + (int)gridDim.x : f;
+                if (!o.gmask || ff >= P.N) continue;
+                const int side = o.kind == T_POOLT ? 2 * o.S : o.S;
+                const char* base = reinterpret_cast<const char*>(o.gmask + (long)ff * o.gmask_bs);
+                for (int i = tid; i < o.Cout * side * side / 32; i += kTcWorkers) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (long)i * 128));
+                if (head) {
+                    const char* b1 = reinterpret_cast<const char*>(o.gsrc + (long)ff * o.gsrc_bs);
+                    for (int i = tid; i < o.Cin * side * side / 32; i += kTcWorkers) asm volatile("prefetch.global.L2 [%0];" ::"l"(b1 + (long)i * 128));
+                    if (o.gmask2) {
+                        const char* b2 = reinterpret_cast<const char*>(o.gmask2 + (long)ff * o.gmask2_bs);
+                        for (int i = tid; i < o.Cin * side * side / 32; i += kTcWorkers) asm volatile("prefetch.global.L2 [%0];" ::"l"(b2 + (long)i * 128));
+                    }
+                }
+            }
+        }
         if (tid < kTcWorkers && P.x) {
             // the input frame: quad 0 = (r, g, b, 0), quad 1 = 0 (the first conv's K chunk is 8 channels wide)
             unsigned char* X = sm + P.x_off;
@@ -967,8 +989,8 @@ int unet_tc_forward(const paig_task* t, const paig_params* p, const Layout& L, c
 // ReLU gate in the epilogue, max-pool / upsample / head adjoints, skip gradients parked on chip) run by the same kernel in
 // its own layout.  0 ok, > 0 error, -1: not applicable (the caller runs unet_fused_backward).
 int unet_tc_backward(const paig_task* t, const paig_params* p, const Layout& L, float* ws, cudaStream_t st) {
-    const char* sw = getenv("PAIG_UNET_TC_BWD");           // read per call, like PAIG_UNET_TC
-    if (!sw || sw[0] == '0' || getenv("PAIG_NO_TCGEN05")) return -1;
+    const char* sw = getenv("PAIG_UNET_TC_BWD");           // PAIG_UNET_TC_BWD=0: the FMA kernel (read per call, like PAIG_UNET_TC)
+    if ((sw && sw[0] == '0') || getenv("PAIG_NO_TCGEN05")) return -1;
     const UNetDesc& u = L.unet;
     const Dims& d = L.d;
     if (t->deep_unet || d.H != 32) return -1;

@@ -365,3 +365,39 @@ def test_transf_layers_and_decoder_method(task):
     frames = net.decoder(loc.to(DEV))
     _close(frames.cpu().numpy(), ref.numpy(), 2e-5)
     assert torch.equal(frames, out[:, -1])
+
+
+@pytest.mark.parametrize("task,B,seed", [("spring_color", 23, 1), ("bouncing_balls", 100, 2)])
+def test_tcgen05_unet_backward_vs_fma_kernel(task, B, seed):
+    """csrc/unet_tc.cu also runs the ShallowUNet backward-data pass of the 32-px tasks on the tensor cores (the op list of the
+    fused FMA planner: transposed convs with the ReLU gate in the epilogue, head / upsample / max-pool adjoints, skip gradients
+    parked in L2).  Same forward, same gates: every parameter gradient of the step must agree with the FMA kernel's to fp32
+    rounding, and the profile must name the kernel that ran.  PAIG_UNET_TC_BWD is read per call."""
+    import ctypes
+    from paig_reproduction_b200 import _lib
+    lib = _lib.load()
+    spec = po.TASKS[task]
+    net = _net(task, spec.seq_len, 3.0)
+    net.load_state_dict(po.init_state_dict(spec, seed), strict=True)
+    x = po.synthetic_frames(spec, B, spec.seq_len, seed).to(DEV)
+    grads, profs = {}, {}
+    prev = os.environ.get("PAIG_UNET_TC_BWD")
+    try:
+        for mode in ("0", "1"):
+            os.environ["PAIG_UNET_TC_BWD"] = mode
+            lib.paig_profile_begin()
+            net.train_step(x)
+            buf = ctypes.create_string_buffer(1 << 16)
+            lib.paig_profile_end(buf, len(buf))
+            profs[mode] = buf.value.decode()
+            grads[mode] = {k: p.grad.detach().cpu().numpy().copy() for k, p in net.named_parameters() if p.grad is not None}
+    finally:
+        if prev is None:
+            os.environ.pop("PAIG_UNET_TC_BWD", None)
+        else:
+            os.environ["PAIG_UNET_TC_BWD"] = prev
+    assert "unet_tc_bwd" in profs["1"] and "unet_fused_bwd" not in profs["1"], profs["1"]
+    assert "unet_fused_bwd" in profs["0"] and "unet_tc_bwd" not in profs["0"], profs["0"]
+    assert sorted(grads["0"]) == sorted(grads["1"])
+    for k in grads["0"]:
+        _close(grads["1"][k], grads["0"][k], 2e-5)
