@@ -370,7 +370,7 @@ def main():
             traffic = None
             try:
                 # DRAM bytes (read + write) of this kernel group per step, from the committed `ncu --set full` capture
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r2s_ncu_traffic.json"))).get(top)
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r2u_ncu_traffic.json"))).get(top)
             except (OSError, ValueError):
                 pass
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
