@@ -707,6 +707,10 @@ int conv3x3_wgrad(const WgradArgs& in_args, float* dW, float* db, cudaStream_t s
     WgradArgs a = in_args;
     if (a.N <= 0) return 0;
     {
+        const int rc = conv3x3_wgrad_tc(in_args, dW, db, st);      // tcgen05 3xTF32 (32 .. 128 channels both sides)
+        if (rc >= 0) return rc;
+    }
+    {
         const int rc = conv3x3_wgrad_tma(in_args, dW, db, st);     // TMA-staged, double-buffered strips when eligible
         if (rc >= 0) return rc;
     }

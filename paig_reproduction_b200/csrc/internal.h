@@ -112,6 +112,8 @@ struct WgradArgs {
 int conv3x3_wgrad(const WgradArgs& a, float* dW, float* db, cudaStream_t st);
 // wgrad_tma.cu: TMA-staged variant; -1 when the layer geometry does not qualify (then conv3x3_wgrad's own kernel runs)
 int conv3x3_wgrad_tma(const WgradArgs& a, float* dW, float* db, cudaStream_t st);
+// wgrad_tc.cu: tcgen05 3xTF32 variant for layers with 32 .. 128 channels on both sides; same return convention
+int conv3x3_wgrad_tc(const WgradArgs& a, float* dW, float* db, cudaStream_t st);
 size_t wgrad_partials_floats(int Cin, int Cout);
 int reduce_partials(const float* partials, int nparts, int stride, int n0, float* out0, int n1, float* out1,
                     cudaStream_t st);
