@@ -21,9 +21,10 @@
 //     split every raw element into hi | lo and write the MMA tiles in the 128-byte-swizzled K-major layout themselves:
 //     16-byte chunks for the gradient rows, scalar stores with lanes along K for the three shifted input copies (both
 //     conflict free).
-//   * 3xTF32 (hi.hi + hi.lo + lo.hi, split as in gemm_tc.cu).  The tensor core accumulates with truncation, so the
-//     hi.hi product runs in chains of kChain K blocks that the converter warps drain into fp32 registers (round to
-//     nearest); the two correction products are 2^-11 of the main one and share one long chain in their own accumulator.
+//   * 3xTF32 (hi.hi + hi.lo + lo.hi, split as in gemm_tc.cu) in two MMAs per K step: [main | corr] += G_hi x [X_hi | X_lo]
+//     (N doubled, one fetch of G_hi -- the kernel is bound by the MMAs' shared-memory operand fetch) and corr += G_lo x X_hi.
+//     The tensor core accumulates with truncation, so the accumulators run in chains of `chain` K blocks that the
+//     converter warps drain into fp32 registers (round to nearest).
 //   * The bias gradient rides along as one extra column: a row of ones appended to the X tile; its products with the
 //     unshifted gradient rows (ky = 1) are sum g.
 //   * grid = (K splits, M tiles, N tiles); every CTA writes its share of partial `split` in the final
@@ -42,13 +43,15 @@
 namespace paig {
 namespace {
 
-constexpr int kWcThreads = 320;        // warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, warps 2..9 converters + drainers
-constexpr int kWcConv = 256;
-constexpr int kWcStages = 2;            // converted (hi | lo) operand stages the MMAs read
+constexpr int kWcConvWarps = 12;       // converter warps (the conversion is latency bound: 8 -> 12 warps 0.69 -> ? us per K block)
+constexpr int kWcThreads = 64 + 32 * kWcConvWarps;   // warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, then the converters
+constexpr int kWcConv = 32 * kWcConvWarps;
+constexpr int kWcDrain = 256;          // the first eight converter warps also drain the main accumulator
+constexpr int kWcStages = 3;            // converted (hi | lo) operand stages the MMAs read (with two, conversion and MMAs of a
+                                        // stage alternate and the kernel runs at the SUM of both)
 constexpr int kWcMaxRaw = 6;           // raw TMA landing stages
 constexpr int kWcMaxCt = 32;           // input channels per N tile
 constexpr unsigned kWcABytes = 128 * 128;
-constexpr unsigned kWcCorrCol = 256;   // TMEM column of the correction accumulator
 
 struct WgTcArgs {
     CUtensorMap tmG, tmIn;
@@ -57,7 +60,7 @@ struct WgTcArgs {
     int bx, by, lbx;          // K block = bx x by pixels (= 32); lbx = log2(bx)
     int bpr, bpf;             // K blocks per row group (S / bx) and per frame (S*S / 32)
     long total_blocks;        // frames * bpf
-    int splits, chain, nraw, dbg;
+    int splits, chain, nraw, nconv, dbg;
     int Ct;                   // input channels per N tile
     int stride;               // floats per partial: 9 Cin Cout + Cout
 };
@@ -132,7 +135,8 @@ __global__ void __launch_bounds__(kWcThreads, 1) conv3x3_wgrad_tc_kernel(const _
     const unsigned rawx_bytes = ((unsigned)(Ct * a.by * rawx * 4) + 1023u) & ~1023u;
     const unsigned raw_bytes = kWcABytes + rawx_bytes;                       // raw stage: gradient boxes | input box
     const unsigned stage_bytes = 2 * kWcABytes + 2 * b_bytes;                // MMA stage: G_hi | G_lo | X_hi | X_lo
-    unsigned char* rbase = base + kWcStages * (size_t)stage_bytes;
+    const int nconv = a.nconv;
+    unsigned char* rbase = base + nconv * (size_t)stage_bytes;
     const int nraw = a.nraw;
     const long kb0 = a.total_blocks * blockIdx.x / a.splits, kb1 = a.total_blocks * (blockIdx.x + 1) / a.splits;
     const int count = (int)(kb1 - kb0);
@@ -141,7 +145,7 @@ __global__ void __launch_bounds__(kWcThreads, 1) conv3x3_wgrad_tc_kernel(const _
         for (int s = 0; s < kWcStages; ++s) { wc_init(&conv[s], kWcConv); wc_init(&empty[s], 1); }
         for (int s = 0; s < kWcMaxRaw; ++s) { wc_init(&rfull[s], 1); wc_init(&rempty[s], kWcConv); }
         wc_init(&chain_done, 1);
-        wc_init(&drained, kWcConv);
+        wc_init(&drained, kWcDrain);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -149,7 +153,7 @@ __global__ void __launch_bounds__(kWcThreads, 1) conv3x3_wgrad_tc_kernel(const _
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     // constant rows: gradient rows past 3 Cout (M padding) are zero; the 16 rows after the X tile are [ones | 15 x zero]
-    for (int s = 0; s < kWcStages; ++s) {
+    for (int s = 0; s < nconv; ++s) {
         float4* st = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
         for (int e = threadIdx.x; e < (128 - rowsA) * 8; e += kWcThreads) {
             st[rowsA * 8 + e] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -201,60 +205,64 @@ __global__ void __launch_bounds__(kWcThreads, 1) conv3x3_wgrad_tc_kernel(const _
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(NT >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+            // per K step two MMAs instead of three: [main | corr] += G_hi x [X_hi | X_lo] (the two X tiles are adjacent rows:
+            // one descriptor, N = 2 NT, one fetch of G_hi) and corr += G_lo x X_hi
+            const unsigned idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)((2 * NT) >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
+            const unsigned idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(NT >> 3) << 17) | ((unsigned)(128 >> 4) << 24);
             int in_chain = 0;
             unsigned drained_ph = 0;
+            int s = 0;
+            unsigned cph = 0;
             for (int i = 0; i < count; ++i) {
-                const int s = i & 1;
-                wc_wait(&conv[s], ((unsigned)(i >> 1)) & 1u);
+                wc_wait(&conv[s], cph);
                 const bool first = in_chain == 0;
                 if (first && i > 0) { wc_wait(&drained, drained_ph); drained_ph ^= 1u; }     // the main accumulator was read out
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const unsigned sa = wc_u32(base + (size_t)s * stage_bytes);
-                const unsigned sa_lo = sa + kWcABytes, sb = sa + 2 * kWcABytes, sb_lo = sb + b_bytes;
+                const unsigned sa_lo = sa + kWcABytes, sb = sa + 2 * kWcABytes;
                 if (!(a.dbg & 1))
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint64_t ah = wc_desc(sa + 32u * k), al = wc_desc(sa_lo + 32u * k);
-                    const uint64_t bh = wc_desc(sb + 32u * k), bl = wc_desc(sb_lo + 32u * k);
-                    wc_mma(tmem, ah, bh, idesc, (first && k == 0) ? 0u : 1u);
-                    wc_mma(tmem + kWcCorrCol, ah, bl, idesc, (i == 0 && k == 0) ? 0u : 1u);
-                    wc_mma(tmem + kWcCorrCol, al, bh, idesc, 1u);
+                    const uint64_t ah = wc_desc(sa + 32u * k), al = wc_desc(sa_lo + 32u * k), bh = wc_desc(sb + 32u * k);
+                    wc_mma(tmem, ah, bh, idesc1, (first && k == 0) ? 0u : 1u);
+                    wc_mma(tmem + (unsigned)NT, al, bh, idesc2, 1u);
                 }
                 wc_commit(&empty[s]);
                 if (++in_chain == chain || i == count - 1) { wc_commit(&chain_done); in_chain = 0; }
+                if (++s == nconv) { s = 0; cph ^= 1u; }
             }
         }
     } else {
-        const int t = threadIdx.x - 64;                                      // 0..255
-        const int q = warp & 3, h = (warp - 2) >> 2;                         // TMEM lane quarter, column half
+        const int t = threadIdx.x - 64;                                      // 0 .. kWcConv-1
+        const bool drainer = warp < 10;                                      // warps 2..9: (TMEM lane quarter, column half)
+        const int q = warp & 3, h = ((warp - 2) >> 2) & 1;
         const int colsPer = NT >> 1;
         float acc[kWcAccMax];
 #pragma unroll
         for (int e = 0; e < kWcAccMax; ++e) acc[e] = 0.f;
         const unsigned tbase = tmem + ((unsigned)(q * 32) << 16) + (unsigned)(h * colsPer);
-        auto drain = [&](int c, unsigned col0) {
+        auto drain = [&](int c) {                                            // acc += main + corr of chain c (both restart per chain)
             wc_wait(&chain_done, (unsigned)c & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
             for (int j = 0; j < kWcAccMax / 8; ++j) {
                 if (j * 8 < colsPer) {
-                    float v[8];
-                    wc_ld8(tbase + col0 + (unsigned)(j * 8), v);
+                    float v[8], u[8];
+                    wc_ld8(tbase + (unsigned)(j * 8), v);
+                    wc_ld8(tbase + (unsigned)(NT + j * 8), u);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[j * 8 + e] += v[e];
+                    for (int e = 0; e < 8; ++e) acc[j * 8 + e] += v[e] + u[e];
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         };
         int pending = -1;
         const int lbx = a.lbx, bxm = a.bx - 1;
-        int rs = 0, in_chain = 0, chain_no = 0;
-        unsigned rph = 0;
+        int rs = 0, in_chain = 0, chain_no = 0, s = 0;
+        unsigned rph = 0, eph = 1;
         for (int i = 0; i < count; ++i) {
-            const int s = i & 1;
             wc_wait(&rfull[rs], rph);
-            wc_wait(&empty[s], (((unsigned)(i >> 1)) & 1u) ^ 1u);           // the MMAs that read this stage two blocks ago retired
+            wc_wait(&empty[s], eph);                                        // the MMAs that last read this stage retired
             unsigned char* st = base + (size_t)s * stage_bytes;
             const unsigned char* rst = rbase + (size_t)rs * raw_bytes;
             if (!(a.dbg & 2))
@@ -262,20 +270,21 @@ __global__ void __launch_bounds__(kWcThreads, 1) conv3x3_wgrad_tc_kernel(const _
                 // 16-byte chunk of every box per thread, the loads of all boxes in flight together
                 const float4* gr = reinterpret_cast<const float4*>(rst);
                 float4* gh = reinterpret_cast<float4*>(st);
-                float4 x[4];
+                constexpr int kTrips = (4 * 256 + kWcConv - 1) / kWcConv;
+                float4 x[kTrips];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (j < nA) x[j] = gr[t + 256 * j];
-                const int row0 = t >> 3, ch = t & 7;
+                for (int j = 0; j < kTrips; ++j)
+                    if (t + kWcConv * j < nA * 256) x[j] = gr[t + kWcConv * j];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < nA) {
+                for (int j = 0; j < kTrips; ++j) {
+                    if (t + kWcConv * j < nA * 256) {
+                        const int e = t + kWcConv * j, ch = e & 7;
                         float4 hh, ll;
                         hh.x = wc_rn(x[j].x); ll.x = wc_rn(x[j].x - hh.x);
                         hh.y = wc_rn(x[j].y); ll.y = wc_rn(x[j].y - hh.y);
                         hh.z = wc_rn(x[j].z); ll.z = wc_rn(x[j].z - hh.z);
                         hh.w = wc_rn(x[j].w); ll.w = wc_rn(x[j].w - hh.w);
-                        const int row = row0 + 32 * j, d = (row << 3) + (ch ^ (row & 7));
+                        const int row = e >> 3, d = (row << 3) + (ch ^ (row & 7));
                         gh[d] = hh;
                         gh[d + kWcABytes / 16] = ll;
                     }
@@ -308,18 +317,20 @@ __global__ void __launch_bounds__(kWcThreads, 1) conv3x3_wgrad_tc_kernel(const _
             wc_arrive(&conv[s]);
             wc_arrive(&rempty[rs]);
             if (++rs == nraw) { rs = 0; rph ^= 1u; }
-            if (pending >= 0) {                                              // the previous chain, drained behind this block's conversion
-                drain(pending, 0u);
+            if (++s == nconv) { s = 0; eph ^= 1u; }
+            if (pending >= 0 && drainer) {                                   // the previous chain, drained behind this block's conversion
+                drain(pending);
                 wc_arrive(&drained);
-                pending = -1;
             }
+            pending = -1;
             if (++in_chain == chain || i == count - 1) { pending = chain_no++; in_chain = 0; }
         }
-        if (pending >= 0) drain(pending, 0u);
-        if (count > 0) drain(pending >= 0 ? pending : 0, kWcCorrCol);        // chain_done's last phase is already complete
+        if (drainer) {
+            drain(pending);                                                  // the last block always closes a chain
+        }
         // ---- write this CTA's share of partial blockIdx.x: rows = (ky, co), columns = (kx, ci) | ones ----
         const int R = m0 + q * 32 + lane;
-        if (R < 3 * a.Cout) {
+        if (drainer && R < 3 * a.Cout) {
             const int ky = R / a.Cout, co = R % a.Cout;
             float* out = a.partials + (size_t)blockIdx.x * a.stride;
             float* ow = out + ((size_t)co * a.Cin + c0) * 9 + ky * 3;
@@ -327,7 +338,7 @@ __global__ void __launch_bounds__(kWcThreads, 1) conv3x3_wgrad_tc_kernel(const _
             for (int e = 0; e < kWcAccMax; ++e) {
                 const int col = h * colsPer + e;
                 if (e < colsPer) {
-                    const float v = count > 0 ? acc[e] : 0.f;
+                    const float v = acc[e];
                     if (col < rowsB) {
                         const int kx = col / Ct, ci = col - kx * Ct;
                         ow[ci * 9 + kx] = v;
@@ -427,17 +438,20 @@ int conv3x3_wgrad_tc(const WgradArgs& w, float* dW, float* db, cudaStream_t st) 
         return -1;
     const int NT = 3 * a.Ct + 16;
     const size_t raw_bytes = kWcABytes + (((size_t)a.Ct * a.by * (a.bx + 8) * 4 + 1023) & ~(size_t)1023);
-    const size_t conv_bytes = kWcStages * (2 * (size_t)kWcABytes + 2 * (size_t)NT * 128);
     static const int raw_env = getenv("PAIG_WGRAD_TC_RAW") ? atoi(getenv("PAIG_WGRAD_TC_RAW")) : kWcMaxRaw;
-    a.nraw = (int)((226 * 1024 - 1024 - conv_bytes) / raw_bytes);
+    static const int conv_env = getenv("PAIG_WGRAD_TC_STAGES") ? atoi(getenv("PAIG_WGRAD_TC_STAGES")) : kWcStages;
+    const size_t conv_stage = 2 * (size_t)kWcABytes + 2 * (size_t)NT * 128, budget = 226 * 1024 - 1024;
+    a.nconv = (conv_env >= 3 && 3 * conv_stage + 2 * raw_bytes <= budget) ? 3 : 2;     // 8-px layers: the raw box is 8 KB, two stages
+    const size_t conv_bytes = a.nconv * conv_stage;
+    a.nraw = (int)((budget - conv_bytes) / raw_bytes);
     if (a.nraw > raw_env) a.nraw = raw_env;
     if (a.nraw > kWcMaxRaw) a.nraw = kWcMaxRaw;
     if (a.nraw < 2) return -1;
     const size_t smem = conv_bytes + a.nraw * raw_bytes + 1024;
     static const bool debug = getenv("PAIG_DEBUG") != nullptr;
     if (debug)
-        fprintf(stderr, "[paig] wgrad_tc %d->%d S=%d N=%d tiles %dx%d (Ct=%d, MMA N=%d) splits=%d blocks/split=%.1f chain=%d raw stages=%d smem=%zu\n",
-                w.Cin, w.Cout, S, w.N, m_tiles, n_tiles, a.Ct, NT, splits, (double)a.total_blocks / splits, a.chain, a.nraw, smem);
+        fprintf(stderr, "[paig] wgrad_tc %d->%d S=%d N=%d tiles %dx%d (Ct=%d, MMA N=%d) splits=%d blocks/split=%.1f chain=%d stages=%d raw stages=%d smem=%zu\n",
+                w.Cin, w.Cout, S, w.N, m_tiles, n_tiles, a.Ct, NT, splits, (double)a.total_blocks / splits, a.chain, a.nconv, a.nraw, smem);
     launch(conv3x3_wgrad_tc_kernel, dim3(splits, m_tiles, n_tiles), dim3(kWcThreads), smem, st, a);
     int rc = check_launch(layer_name("conv3x3_wgrad_tc", w.Cin, w.Cout, S));
     if (rc) return rc;

@@ -267,3 +267,37 @@ def test_tcgen05_unet_forward_vs_fma_kernel_and_float64(be, task, B, seed):
         assert abs(bias) < (2e-6 if name == "c13" else 8e-7), (name, bias)          # c13: logits, differences of large terms
         checked += 1
     assert checked >= 10
+
+
+@pytest.mark.parametrize("N,Cin,Cout,S", [
+    (3, 32, 32, 32), (5, 64, 32, 32), (2, 32, 32, 64), (7, 64, 64, 16), (6, 32, 64, 16), (5, 96, 64, 16), (9, 128, 128, 8),
+    (8, 64, 128, 8), (6, 128, 32, 16), (40, 32, 32, 8),
+    (300, 32, 32, 32), (150, 64, 64, 16),         # several accumulator chains per CTA (drains), hundreds of K blocks per split
+])
+def test_tcgen05_weight_gradient_vs_float64(be, N, Cin, Cout, S):
+    """csrc/wgrad_tc.cu: the weight / bias gradient of the 64-px UNet's wide layers (blocks.py:113-170) as ONE 3xTF32 tcgen05
+    product of row-shifted gradient rows x column-shifted input rows.  Against float64 it must be as close as an fp32 sum gets
+    (the tensor core's truncating accumulate is kept to short chains drained into fp32 registers: no coherent shrink), on
+    every geometry (32 px: one image row per K block; 64 px: half rows; 16 / 8 px: 2 / 4 rows), with partially filled M tiles
+    (Cout = 32, 64), several N tiles (Cin = 64 .. 128) and a 48-channel N tile (Cin = 96)."""
+    import ctypes
+    g = torch.Generator().manual_seed(S * 1000 + Cin * 10 + Cout)
+    x = torch.randn(N, Cin, S, S, generator=g)
+    x = torch.relu(x) + 0.01 * x                                     # mostly positive, like post-ReLU activations
+    dy = torch.randn(N, Cout, S, S, generator=g) + 0.3               # a coherent part: a truncation bias would show
+    xd, dyd = be.dev(x.numpy()), be.dev(dy.numpy())
+    wd = be.zeros((Cout, Cin, 3, 3))
+    dw, db = be.full((Cout, Cin, 3, 3), 3.0), be.full((Cout,), 3.0)
+    ws = be.zeros(296 * (Cout * Cin * 9 + Cout) + 64)
+    be.lib.paig_profile_begin()
+    be.check(be.lib.paig_conv3x3_backward(xd.ptr, wd.ptr, None, dyd.ptr, None, dw.ptr, db.ptr, N, Cin, Cout, S, 0, ws.ptr,
+                                          be.stream))
+    buf = ctypes.create_string_buffer(1 << 14)
+    be.lib.paig_profile_end(buf, len(buf))
+    assert "conv3x3_wgrad_tc" in buf.value.decode(), buf.value.decode()       # the tensor-core kernel is what ran
+    rw = torch.nn.grad.conv2d_weight(x.double(), (Cout, Cin, 3, 3), dy.double(), padding=1).numpy()
+    rb = dy.double().sum((0, 2, 3)).numpy()
+    ew, eb = sc.rel(dw.np(), rw), sc.rel(db.np(), rb)
+    assert ew < 3e-6 and eb < 3e-6, (ew, eb)
+    signed = float(((dw.np().astype(np.float64) - rw) * np.sign(rw) / np.abs(rw).max()).mean())
+    assert abs(signed) < 1.5e-6, signed
