@@ -226,7 +226,8 @@ def main():
     ws = net._workspace(T, B_PER_GPU, fresh=False)
     params = net._params_now()
     P, G = net._param_table(params), net._param_table(net._grad_views)
-    losses_host = torch.empty(4).pin_memory()
+    losses_host = torch.empty(2, 4).pin_memory()  # one row per in-flight step
+    done = [torch.cuda.Event(), torch.cuda.Event()]
 
     copy_stream = torch.cuda.Stream(dev)
 
@@ -234,27 +235,40 @@ def main():
         _lib.check(lib.paig_stage_input_host(ctypes.byref(tk), host_pool[i % POOL].data_ptr(), B_PER_GPU, i % 2, ws.data_ptr(),
                                              copy_stream.cuda_stream))
 
-    def step_host(i):
-        # every step: its own input comes from pinned host memory (staged one step ahead so the copy hides under the
-        # previous step's kernels), the four losses go back to the host and are read before the next step starts
-        stage(i + 1)
+    seen = []
+
+    def step_host(i, first):
+        # every step: its own input comes from pinned host memory and its four losses go back to the host and are READ by
+        # the caller -- one step behind, the way a training loop logs: step i is enqueued, then the host waits for step
+        # i-1, reads its losses, and only then (its input slot is free again) stages batch i+1 under step i's kernels
         armed = dp.arm()
         _lib.check(lib.paig_step_fused_staged(ctypes.byref(tk), ctypes.byref(P), ctypes.byref(G), B_PER_GPU, i % 2,
-                                              losses_host.data_ptr(), ws.data_ptr(), stream.cuda_stream))
+                                              losses_host[i % 2].data_ptr(), ws.data_ptr(), stream.cuda_stream))
         dp.reduce(armed)
-        stream.synchronize()                      # the caller reads the losses every step
-        return float(losses_host[0])
+        done[i % 2].record(stream)
+        if not first:
+            done[(i - 1) % 2].synchronize()
+            seen.append(float(losses_host[(i - 1) % 2][0]))
+        stage(i + 1)
+
+    def drain_host(i):                            # the last step's losses
+        done[i % 2].synchronize()
+        seen.append(float(losses_host[i % 2][0]))
 
     stage(0)
     for i in range(3):
-        step_host(i)
+        step_host(i, i == 0)
+    drain_host(2)
     barrier()
+    seen.clear()
     t0 = time.perf_counter()
     e0.record(stream)
     for i in range(3, 3 + args.steps):            # the batch counter runs on: slot (i % 2) holds batch i
-        step_host(i)
+        step_host(i, i == 3)
+    drain_host(3 + args.steps - 1)
     e1.record(stream)
     barrier()
+    assert len(seen) == args.steps and all(v == v for v in seen), "e2e: every step's losses must have been read"
     ms_e2e = torch.tensor([max(e0.elapsed_time(e1), 0.0)], device=dev)
     if world > 1:
         dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
@@ -403,7 +417,7 @@ def main():
                 "clocks": sampler.summary(),
                 "e2e": {"value": e2e_val, "unit": "sequences/s", "h2d_bytes_per_step": B_PER_GPU * T * 3 * H * H * 4,
                         "d2h_bytes_per_step": 16, "ms_per_step": ms_e2e / args.steps,
-                        "api": "paig_stage_input_host + paig_step_fused_staged (pinned host input of every step copied on a side stream one step ahead, losses read back every step)"},
+                        "api": "paig_stage_input_host + paig_step_fused_staged (pinned host input of every step copied on a side stream one step ahead; the losses of every step copied back and read by the host one step behind, so the next step is already enqueued while the host waits)"},
                 "gpu_launches": int(launches),
                 "gpu_launches_per_step": launches / args.steps,
                 "roofline": roof,
