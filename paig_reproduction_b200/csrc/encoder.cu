@@ -512,6 +512,59 @@ __global__ void __launch_bounds__(256) gather_frames_kernel(const float4* __rest
 // CTA write their share of dW2 / dW3 / db2 / db3 to a partial block (folded in fixed order by reduce_partials_batch)
 // and dH1 (gated by l1's ReLU) for the l1 backward GEMMs.
 constexpr int kTailRows = 16;
+// W2 lives in shared memory as [unit j][k] with rows padded to 204 floats: a row starts on a 16-byte boundary and the
+// 16-byte loads of 8 consecutive units (row pitch 816 B = 12 banks mod 32) touch 8 distinct bank quads.  Both kernels keep
+// the summation order of the scalar loops they replaced (k, r, j ascending), so results did not change bit for bit; what
+// changed is the shared-memory traffic: 16-byte operand loads and register tiles instead of one 4-byte load per FMA
+// (forward 40 -> ? us, backward 72 -> ? us at M = 2000; both were bound by the LSU pipe and by 4-byte global loads of W2).
+constexpr int kTailPitch = 204;
+
+// Loads are issued in batches of 8 (W2) / 4 (activation rows) per thread before the first store: one load per trip left the
+// ~700-cycle L2 latency exposed 40 times over (W2 alone: 14 us of the 37 us forward kernel).
+__device__ __forceinline__ void tail_load_w2(float* sW2, const float* __restrict__ W2, int tid) {
+    constexpr int HID = kHidden, NV = HID * HID / 4;
+    if ((reinterpret_cast<uintptr_t>(W2) & 15) == 0) {
+        const float4* src = reinterpret_cast<const float4*>(W2);
+        for (int b = 0; b < NV; b += 8 * 256) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = b + u * 256 + tid;
+                if (i < NV) v[u] = src[i];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = b + u * 256 + tid;
+                if (i < NV) {
+                    const int j = i / (HID / 4), c = i - j * (HID / 4);
+                    *reinterpret_cast<float4*>(sW2 + j * kTailPitch + 4 * c) = v[u];
+                }
+            }
+        }
+    } else {
+        for (int i = tid; i < HID * HID; i += 256) sW2[(i / HID) * kTailPitch + i % HID] = W2[i];
+    }
+}
+// kTailRows rows of a [M][200] activation (rows past M read as zero) into a dense [16][200] shared array
+__device__ __forceinline__ void tail_load_rows(float* dst, const float* __restrict__ src, int r0, int M, int tid) {
+    constexpr int HID = kHidden, R = kTailRows, NV = R * HID / 4;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = u * 256 + tid, r = i / (HID / 4);
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < NV && r0 + r < M) v[u] = reinterpret_cast<const float4*>(src + (long)r0 * HID)[i];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = u * 256 + tid;
+            if (i < NV) reinterpret_cast<float4*>(dst)[i] = v[u];
+        }
+    } else {
+        for (int i = tid; i < R * HID; i += 256) dst[i] = r0 + i / HID < M ? src[(long)(r0 + i / HID) * HID + i % HID] : 0.f;
+    }
+}
 
 __global__ void __launch_bounds__(256) enc_tail_fwd_kernel(const float* __restrict__ H1, int M, int N, int n, float half,
                                                            const float* __restrict__ W2, const float* __restrict__ b2,
@@ -520,21 +573,28 @@ __global__ void __launch_bounds__(256) enc_tail_fwd_kernel(const float* __restri
                                                            float* __restrict__ enc_pos, float* __restrict__ enc_pos2) {
     constexpr int HID = kHidden, R = kTailRows;
     PAIG_DYN_SMEM(float, smem);
-    float* sW2t = smem;                                   // [k][j]
-    float (*sH1)[HID] = reinterpret_cast<float (*)[HID]>(sW2t + HID * HID);
+    float* sW2 = smem;                                    // [j][k], rows of kTailPitch
+    float (*sH1)[HID] = reinterpret_cast<float (*)[HID]>(sW2 + HID * kTailPitch);
     float (*sH2)[HID] = reinterpret_cast<float (*)[HID]>(&sH1[R][0]);
     const int tid = threadIdx.x, r0 = blockIdx.x * R;
-    for (int i = tid; i < HID * HID; i += 256) sW2t[(i % HID) * HID + i / HID] = W2[i];
-    for (int i = tid; i < R * HID; i += 256) sH1[i / HID][i % HID] = r0 + i / HID < M ? H1[(long)(r0 + i / HID) * HID + i % HID] : 0.f;
+    tail_load_w2(sW2, W2, tid);
+    tail_load_rows(&sH1[0][0], H1, r0, M, tid);
     __syncthreads();
     if (tid < HID) {
         float acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = 0.f;
-        for (int k = 0; k < HID; ++k) {
-            const float w = sW2t[k * HID + tid];
+        const float* wrow = sW2 + tid * kTailPitch;
+        for (int k = 0; k < HID; k += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(wrow + k);
 #pragma unroll
-            for (int r = 0; r < R; ++r) acc[r] += sH1[r][k] * w;
+            for (int r = 0; r < R; ++r) {
+                const float4 h = *reinterpret_cast<const float4*>(&sH1[r][k]);      // warp-wide broadcast
+                acc[r] += h.x * w.x;
+                acc[r] += h.y * w.y;
+                acc[r] += h.z * w.z;
+                acc[r] += h.w * w.w;
+            }
         }
         const float bb = b2[tid];
 #pragma unroll
@@ -567,19 +627,15 @@ __global__ void __launch_bounds__(256) enc_tail_bwd_kernel(const float* __restri
                                                            float* __restrict__ partials, int stride) {
     constexpr int HID = kHidden, R = kTailRows;
     PAIG_DYN_SMEM(float, smem);
-    float* sW2 = smem;                                    // [j][k]
-    float (*sH1)[HID] = reinterpret_cast<float (*)[HID]>(sW2 + HID * HID);
+    float* sW2 = smem;                                    // [j][k], rows of kTailPitch
+    float (*sH1)[HID] = reinterpret_cast<float (*)[HID]>(sW2 + HID * kTailPitch);
     float (*sH2)[HID] = reinterpret_cast<float (*)[HID]>(&sH1[R][0]);
     float (*sDz2)[HID] = reinterpret_cast<float (*)[HID]>(&sH2[R][0]);
     float (*sDo3)[2] = reinterpret_cast<float (*)[2]>(&sDz2[R][0]);
     const int tid = threadIdx.x, r0 = blockIdx.x * R;
-    for (int i = tid; i < HID * HID; i += 256) sW2[i] = W2[i];
-    for (int i = tid; i < R * HID; i += 256) {
-        const int r = i / HID, k = i % HID;
-        const bool ok = r0 + r < M;
-        sH1[r][k] = ok ? H1[(long)(r0 + r) * HID + k] : 0.f;
-        sH2[r][k] = ok ? H2[(long)(r0 + r) * HID + k] : 0.f;
-    }
+    tail_load_w2(sW2, W2, tid);
+    tail_load_rows(&sH1[0][0], H1, r0, M, tid);
+    tail_load_rows(&sH2[0][0], H2, r0, M, tid);
     if (tid < R * 2) {
         const int r = tid >> 1, c = tid & 1, row = r0 + r;
         float v = 0.f;
@@ -613,31 +669,62 @@ __global__ void __launch_bounds__(256) enc_tail_bwd_kernel(const float* __restri
         ob3[tid] = s;
     }
     __syncthreads();
-    for (int i = tid; i < HID * HID; i += 256) {                  // this chunk's share of dW2[j][k]
-        const int j = i / HID, k = i % HID;
-        float s = 0.f;
+    // this chunk's share of dW2[j][k] = sum_r dZ2[r][j] H1[r][k]: thread = (20 units j) x (4 columns k), two passes
+    if (tid < 250) {
+        const int k4 = tid % 50, jg = tid / 50;
+        for (int pass = 0; pass < 2; ++pass) {
+            const int j0 = jg * 40 + pass * 20;
+            float4 acc[20];
 #pragma unroll
-        for (int r = 0; r < R; ++r) s += sDz2[r][j] * sH1[r][k];
-        out[i] = s;
+            for (int jj = 0; jj < 20; ++jj) acc[jj] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+            for (int r = 0; r < R; ++r) {
+                const float4 h = *reinterpret_cast<const float4*>(&sH1[r][4 * k4]);
+#pragma unroll
+                for (int jj = 0; jj < 20; ++jj) {
+                    const float dz = sDz2[r][j0 + jj];
+                    acc[jj].x += dz * h.x;
+                    acc[jj].y += dz * h.y;
+                    acc[jj].z += dz * h.z;
+                    acc[jj].w += dz * h.w;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 20; ++jj) {
+                float* o = out + (j0 + jj) * HID + 4 * k4;
+                o[0] = acc[jj].x; o[1] = acc[jj].y; o[2] = acc[jj].z; o[3] = acc[jj].w;
+            }
+        }
     }
     if (tid < HID) {
         float s = 0.f;
 #pragma unroll
         for (int r = 0; r < R; ++r) s += sDz2[r][tid];
         ob2[tid] = s;
-    }
-    // dH1 = (dZ2 W2) gated by l1's ReLU
-    for (int i = tid; i < R * HID; i += 256) {
-        const int r = i / HID, k = i % HID;
-        if (r0 + r >= M) continue;
-        float s = 0.f;
-        for (int j = 0; j < HID; ++j) s += sW2[j * HID + k] * sDz2[r][j];
-        dH1[(long)(r0 + r) * HID + k] = sH1[r][k] > 0.f ? s : 0.f;
+        // dH1 = (dZ2 W2) gated by l1's ReLU: thread = column k, all 16 rows in registers
+        float acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.f;
+        for (int j = 0; j < HID; j += 4) {
+            const float w0 = sW2[(j + 0) * kTailPitch + tid], w1 = sW2[(j + 1) * kTailPitch + tid];
+            const float w2 = sW2[(j + 2) * kTailPitch + tid], w3 = sW2[(j + 3) * kTailPitch + tid];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const float4 dz = *reinterpret_cast<const float4*>(&sDz2[r][j]);    // warp-wide broadcast
+                acc[r] += w0 * dz.x;
+                acc[r] += w1 * dz.y;
+                acc[r] += w2 * dz.z;
+                acc[r] += w3 * dz.w;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (r0 + r < M) dH1[(long)(r0 + r) * HID + tid] = sH1[r][tid] > 0.f ? acc[r] : 0.f;
     }
 }
 
 static size_t enc_tail_smem(bool bwd) {
-    return ((size_t)kHidden * kHidden + (size_t)kTailRows * kHidden * (bwd ? 3 : 2) + (bwd ? kTailRows * 2 : 0)) * sizeof(float);
+    return ((size_t)kHidden * kTailPitch + (size_t)kTailRows * kHidden * (bwd ? 3 : 2) + (bwd ? kTailRows * 2 : 0)) * sizeof(float);
 }
 constexpr int kTailStride = kHidden * kHidden + 2 * kHidden + kHidden + 4;      // floats per CTA partial
 
