@@ -449,7 +449,7 @@ int gemm_tc_partials(const float* A, const float* B, int M, int N, int K, bool f
     const int tiles = cdiv(M, kTcBM) * cdiv(N, a.BN);
     int splits;
     if (fixed_split) splits = nkb >= 24 ? nkb / 12 : 1;                 // by K only: batch-invariant summation order
-    else splits = tiles >= 120 ? 1 : (148 + tiles - 1) / tiles;
+    else splits = tiles >= 120 ? 1 : (148 / tiles > 0 ? 148 / tiles : 1);     // one resident wave: 24 tiles x 7 splits = 168 CTAs ran as 148 + 20
     if (splits > nkb / 2) splits = nkb / 2 > 0 ? nkb / 2 : 1;
     while (splits > 1 && (size_t)splits * M * N > partial_floats) --splits;
     if ((size_t)splits * M * N > partial_floats) return -1;
