@@ -9,8 +9,9 @@
 // backward GEMMs).  One CTA per 128 x BN output tile and K range (split-K over gridDim.z):
 //   warp 0      TMA producer: 2-D tensor maps, 128-byte swizzle, boxes of 32 floats (one swizzle span) x rows; two
 //               stages on full/empty mbarriers
-//   warps 2-5   split each landed stage in place into hi (over the raw tile) and lo (a second tile with the identical
-//               swizzled byte layout, so no address arithmetic), then fence.proxy.async and arrive
+//   warps 2-9   split each landed stage in place into hi (over the raw tile) and lo (a second tile with the identical
+//               swizzled byte layout, so no address arithmetic), then fence.proxy.async and arrive (the drained kernel:
+//               warps 6-9 convert, warps 2-5 drain the accumulator, so the two overlap)
 //   warp 1      allocates TMEM (256 columns), issues 4 K-steps x 3 tcgen05.mma.kind::tf32 per stage from one thread
 //               (M=128, N=BN, K=8, fp32 accumulate in TMEM) and commits to the stage's empty barrier
 //   warps 2-5   epilogue: tcgen05.ld 32x32b (a warp owns its 32 TMEM lanes = 32 rows), write the split's partial tile;
@@ -29,7 +30,8 @@
 
 namespace paig {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;      // warp 0 TMA, warp 1 MMA issue, warps 2..9 converters (2..5 also own the TMEM lane quarters)
+constexpr int kTcConv = 256;
 constexpr int kTcBM = 128, kTcBK = 32, kTcStages = 2;
 
 struct TcArgs {
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_kernel(const __grid
     const int count = min(a.kb_per, nkb - kb0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], kTcConv); mbar_init(&empty[s], 1); }
         mbar_init(&done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -150,24 +152,36 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_kernel(const __grid
             umma_commit(&done);
         }
     } else {
-        const int t = threadIdx.x - 64;                                  // 0..127
+        const int t = threadIdx.x - 64;                                  // 0..255
         for (int i = 0; i < count; ++i) {
             const int s = i % kTcStages;
             mbar_wait(&full[s], ((unsigned)(i / kTcStages)) & 1u);
             float4* st = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
             const int a4 = a_bytes / 16, b4 = b_bytes / 16;
-            // A_hi | A_lo occupy [0, a4) and [a4, 2 a4); B_hi | B_lo follow
-            for (int e = t; e < a4 + b4; e += 128) {
-                float4* hi = e < a4 ? st + e : st + 2 * a4 + (e - a4);
-                float4* lo = e < a4 ? hi + a4 : hi + b4;
-                const float4 x = *hi;
-                float4 h, l;
-                h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
-                h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
-                h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
-                h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
-                *hi = h;
-                *lo = l;
+            // A_hi | A_lo occupy [0, a4) and [a4, 2 a4); B_hi | B_lo follow.  Four loads in flight per thread: one load per
+            // trip left the converters -- which bound this kernel -- waiting out a shared-memory round trip per 16 bytes
+            for (int e0 = t; e0 < a4 + b4; e0 += 4 * kTcConv) {
+                float4 x[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * kTcConv;
+                    if (e < a4 + b4) x[u] = *(e < a4 ? st + e : st + 2 * a4 + (e - a4));
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = e0 + u * kTcConv;
+                    if (e < a4 + b4) {
+                        float4* hi = e < a4 ? st + e : st + 2 * a4 + (e - a4);
+                        float4* lo = e < a4 ? hi + a4 : hi + b4;
+                        float4 h, l;
+                        h.x = tf32_rn(x[u].x); l.x = tf32_rn(x[u].x - h.x);
+                        h.y = tf32_rn(x[u].y); l.y = tf32_rn(x[u].y - h.y);
+                        h.z = tf32_rn(x[u].z); l.z = tf32_rn(x[u].z - h.z);
+                        h.w = tf32_rn(x[u].w); l.w = tf32_rn(x[u].w - h.w);
+                        *hi = h;
+                        *lo = l;
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the tensor core
             mbar_arrive(&conv[s]);
@@ -178,7 +192,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_kernel(const __grid
         const int q = warp & 3;
         const int row = m0 + q * 32 + lane;
         float* out = a.partials + ((size_t)blockIdx.z * a.M + row) * a.N + n0;
-        for (int c = 0; c < BN; c += 16) {
+        const int chalf = ((BN / 16 + 1) / 2) * 16;                      // warps 2..5 take columns [0, chalf), warps 6..9 the rest
+        for (int c = warp < 6 ? 0 : chalf; c < (warp < 6 ? chalf : BN); c += 16) {
             unsigned v[16];
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
@@ -231,7 +246,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_drained_kernel(cons
     const int count = min(a.kb_per, nkb - kb0);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&conv[s], 128); mbar_init(&empty[s], 1); }   // 128 converter threads
         for (int b = 0; b < 2; ++b) { mbar_init(&accfull[b], 1); mbar_init(&accfree[b], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -283,14 +298,49 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_drained_kernel(cons
                 umma_commit(&accfull[b]);
             }
         }
+    } else if (warp >= 6) {
+        // ===== converters (warps 6..9): split each landed stage in place into hi | lo =====
+        const int t = threadIdx.x - 192;                                 // 0..127
+        for (int i = 0; i < count; ++i) {
+            const int s = i % kTcStages;
+            mbar_wait(&full[s], ((unsigned)(i / kTcStages)) & 1u);
+            float4* st = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
+            constexpr int a4 = a_bytes / 16, b4 = b_bytes / 16;
+            for (int e0 = t; e0 < a4 + b4; e0 += 5 * 128) {              // 15 chunks per thread: 3 trips of 5 loads in flight
+                float4 x[5];
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const int e = e0 + u * 128;
+                    if (e < a4 + b4) x[u] = *(e < a4 ? st + e : st + 2 * a4 + (e - a4));
+                }
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const int e = e0 + u * 128;
+                    if (e < a4 + b4) {
+                        float4* hi = e < a4 ? st + e : st + 2 * a4 + (e - a4);
+                        float4* lo = e < a4 ? hi + a4 : hi + b4;
+                        float4 h, l;
+                        h.x = tf32_rn(x[u].x); l.x = tf32_rn(x[u].x - h.x);
+                        h.y = tf32_rn(x[u].y); l.y = tf32_rn(x[u].y - h.y);
+                        h.z = tf32_rn(x[u].z); l.z = tf32_rn(x[u].z - h.z);
+                        h.w = tf32_rn(x[u].w); l.w = tf32_rn(x[u].w - h.w);
+                        *hi = h;
+                        *lo = l;
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive(&conv[s]);
+        }
     } else {
-        const int t = threadIdx.x - 64;                                  // 0..127
+        // ===== drainers (warps 2..5, TMEM lane quarter = warp % 4): after every stage the hi.hi accumulator goes into
+        // register sums; in their own warps the drain of stage i overlaps the conversion of stage i+1 and the MMAs of i+1 =====
         const int q = warp & 3;
         const unsigned lane_base = tmem + ((unsigned)(q * 32) << 16);
         float sum[BN];
 #pragma unroll
         for (int c = 0; c < BN; ++c) sum[c] = 0.f;
-        auto drain = [&](int i) {
+        for (int i = 0; i < count; ++i) {
             const unsigned b = (unsigned)i & 1u, use = (unsigned)i >> 1;
             mbar_wait(&accfull[b], use & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -307,29 +357,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_drained_kernel(cons
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&accfree[b]);
-        };
-        for (int i = 0; i < count; ++i) {
-            const int s = i % kTcStages;
-            mbar_wait(&full[s], ((unsigned)(i / kTcStages)) & 1u);
-            float4* st = reinterpret_cast<float4*>(base + (size_t)s * stage_bytes);
-            constexpr int a4 = a_bytes / 16, b4 = b_bytes / 16;
-            for (int e = t; e < a4 + b4; e += 128) {
-                float4* hi = e < a4 ? st + e : st + 2 * a4 + (e - a4);
-                float4* lo = e < a4 ? hi + a4 : hi + b4;
-                const float4 x = *hi;
-                float4 h, l;
-                h.x = tf32_rn(x.x); l.x = tf32_rn(x.x - h.x);
-                h.y = tf32_rn(x.y); l.y = tf32_rn(x.y - h.y);
-                h.z = tf32_rn(x.z); l.z = tf32_rn(x.z - h.z);
-                h.w = tf32_rn(x.w); l.w = tf32_rn(x.w - h.w);
-                *hi = h;
-                *lo = l;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_arrive(&conv[s]);
-            if (i > 0) drain(i - 1);                                     // the previous stage's MMAs run meanwhile
         }
-        if (count > 0) drain(count - 1);
         // the last commit also covered the correction accumulator
 #pragma unroll
         for (int c = 0; c < BN; c += 16) {
