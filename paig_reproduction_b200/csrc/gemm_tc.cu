@@ -373,9 +373,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) gemm_tf32x3_drained_kernel(cons
         const int row = m0 + q * 32 + lane;
         if (row < a.M) {
             float* out = a.partials + ((size_t)blockIdx.z * a.M + row) * a.N + n0;
+            // 16-byte stores where the row allows (ncu: lg_throttle was this kernel's third stall -- 112 scalar stores per
+            // thread, every one touching 32 sectors per warp)
+            const bool vec = (a.N % 4) == 0 && (reinterpret_cast<uintptr_t>(a.partials) % 16) == 0;
 #pragma unroll
-            for (int c = 0; c < BN; ++c)
-                if (n0 + c < a.N) out[c] = sum[c];
+            for (int c = 0; c < BN; c += 4) {
+                if (vec && n0 + c + 3 < a.N) {
+                    *reinterpret_cast<float4*>(out + c) = make_float4(sum[c], sum[c + 1], sum[c + 2], sum[c + 3]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (n0 + c + e < a.N) out[c + e] = sum[c + e];
+                }
+            }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
