@@ -356,6 +356,14 @@ def main():
         name, cnt, tot = ln.rsplit(" ", 2)
         kern[name] = {"launches_per_step": int(cnt) / prof_steps, "ms_per_step": float(tot) / prof_steps}
     kernel_ms = sum(v["ms_per_step"] for v in kern.values())
+    # the 12 weight-gradient launches of a step are one group for the roofline whichever kernel a layer takes (the 32 -> 32
+    # layer c6 runs on the tcgen05 kernel of csrc/wgrad_tc.cu, the rest on the TMA / mma.sync kernels of csrc/wgrad_tma.cu)
+    wg_tc = kern.pop("conv3x3_wgrad_tc", None)
+    if wg_tc and "conv3x3_wgrad" in kern:
+        kern["conv3x3_wgrad"] = {"launches_per_step": kern["conv3x3_wgrad"]["launches_per_step"] + wg_tc["launches_per_step"],
+                                 "ms_per_step": kern["conv3x3_wgrad"]["ms_per_step"] + wg_tc["ms_per_step"]}
+    elif wg_tc:
+        kern["conv3x3_wgrad_tc"] = wg_tc
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -384,7 +392,7 @@ def main():
             traffic = None
             try:
                 # DRAM bytes (read + write) of this kernel group per step, from the committed `ncu --set full` capture
-                traffic = json.load(open(os.path.join(ROOT, "profiles", "r2u_ncu_traffic.json"))).get(top)
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "r2z_ncu_traffic.json"))).get(top)
             except (OSError, ValueError):
                 pass
             roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -393,7 +401,7 @@ def main():
                              "products, so the tensor pipe does 3x the algorithmic FLOPs counted here); of the nominal FP32-FMA "
                              "peak %.1f TFLOP/s the algorithmic rate is %.3f" % (
                                  {"unet_tc_fwd": "tcgen05 3xTF32 persistent kernel", "unet_tc_bwd": "tcgen05 3xTF32 persistent kernel",
-                                  "conv3x3_wgrad": "12 launches: mma.sync 3xTF32 for layers with 16-channel m-tiles, FP32 FMA for the rest"
+                                  "conv3x3_wgrad": "12 launches: mma.sync 3xTF32 for layers with 16-channel m-tiles, tcgen05 3xTF32 for the 32 -> 32 layer, FP32 FMA for the rest"
                                   }.get(top, "fp32 CUDA-core kernel"), FP32_FMA_NOMINAL_TFLOPS, ach / FP32_FMA_NOMINAL_TFLOPS)),
                     "share_of_step": kern[top]["ms_per_step"] / kernel_ms if kernel_ms else None,
                     "algorithmic_flops_per_step": flops[top], "kernel_ms_per_step": kern[top]["ms_per_step"],
