@@ -291,6 +291,31 @@ def main():
             dist.all_reduce(ms_sus, op=dist.ReduceOp.MAX)
         extras["sustained"] = {"steps": n_sus, "seconds": float(ms_sus.item()) * 1e-3,
                                "value": B_PER_GPU * world * n_sus / (float(ms_sus.item()) * 1e-3), "unit": "sequences/s"}
+        # (1b) the same step replayed from CUDA graphs (PhysicsNet.train_step_graph: one graph per input buffer of the
+        #      pool, side streams inside the capture; the all-reduce of a multi-GPU run stays outside the graph)
+        try:
+            def graph_step(i):
+                net.train_step_graph(dev_pool[i % POOL])
+                dp.reduce(False)
+            for i in range(POOL + 3):
+                graph_step(i)
+            barrier()
+            rl0 = getattr(net, "graph_replay_launches", 0)
+            e0.record(stream)
+            for i in range(args.steps):
+                graph_step(i)
+            e1.record(stream)
+            barrier()
+            ms_g = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms_g, op=dist.ReduceOp.MAX)
+            ok = all(v is not False for v in net._step_graphs.values())
+            extras["cuda_graph"] = {"value": B_PER_GPU * world * args.steps / (float(ms_g.item()) * 1e-3), "unit": "sequences/s",
+                                    "ms_per_step": float(ms_g.item()) / args.steps, "recorded": bool(ok),
+                                    "launches_replayed_per_step": (getattr(net, "graph_replay_launches", 0) - rl0) / args.steps,
+                                    "api": "PhysicsNet.train_step_graph (paig_step_fused recorded once per input buffer, replayed)"}
+        except Exception as exc:                      # noqa: BLE001 -- an extra key must never cost the bench line
+            extras["cuda_graph"] = {"error": str(exc)[:200]}
         # (2) the reference's own call sequence on the drop-in module (what base.py:142-151 / :195 does):
         #     net.output = net(inp); loss, _ = net.compute_loss(); loss.backward()  -- frames materialised, torch autograd
         def dropin_step(i):

@@ -58,8 +58,10 @@ typedef struct paig_wb {
 } paig_wb;
 
 /* Parameter table: pointers into the caller's tensors, named after the reference state_dict.  The same
- * struct type is used for the gradient table (each entry receives dL/dparam; all entries are WRITTEN,
- * not accumulated, by paig_step_backward / paig_step_fused). */
+ * struct type is used for the gradient table (each entry receives dL/dparam; every entry on the step's graph is
+ * WRITTEN, not accumulated, by paig_step_backward / paig_step_fused.  Not on the graph, hence left untouched: vel[*]
+ * when input_steps == 1 (physics_models.py:222-223: the initial velocity is zeros), vel[*] and the physics constants
+ * in STALE mode (d_output_seq == NULL), dt always; NULL entries are skipped). */
 typedef struct paig_params {
     paig_wb content_l1, content_l2;         /* var_net_content.l1/.l2        blocks.py:311-322 */
     paig_wb background_l1, background_l2;   /* var_net_background.l1/.l2 */

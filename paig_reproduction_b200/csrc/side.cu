@@ -29,11 +29,16 @@ thread_local bool g_active = false;
 Side* side_begin(cudaStream_t main) {
     static const bool off = getenv("PAIG_NO_SIDE_STREAMS") != nullptr;
     if (off || g_profiling || g_active) return nullptr;          // per-launch timing wants one launch at a time
+    // Under stream capture (the caller records the step into a CUDA graph) the side streams join the capture through
+    // the fork / join events, which is legal as long as every fork is joined before the capture ends -- the fused step
+    // does that.  PAIG_SIDE_IN_CAPTURE=0 keeps a captured step on one stream.
+    static const bool in_capture = !(getenv("PAIG_SIDE_IN_CAPTURE") && getenv("PAIG_SIDE_IN_CAPTURE")[0] == '0');
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(main, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    if (cudaStreamIsCapturing(main, &cap) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
+    if (cap != cudaStreamCaptureStatusNone && !in_capture) return nullptr;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return nullptr;
     SideSet& set = g_sets[dev];

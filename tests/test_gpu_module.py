@@ -401,3 +401,37 @@ def test_tcgen05_unet_backward_vs_fma_kernel(task, B, seed):
     assert sorted(grads["0"]) == sorted(grads["1"])
     for k in grads["0"]:
         _close(grads["1"][k], grads["0"][k], 2e-5)
+
+
+def test_train_step_graph_replays_bit_identically_and_follows_parameter_updates():
+    """PhysicsNet.train_step_graph: the fused step recorded into a CUDA graph (side streams inside the capture).  A replay
+    gives bit-identical gradients and losses to the eager step on the same input; an in-place parameter update is seen by
+    the next replay (the graph bakes in addresses, not values); a different input buffer records its own graph."""
+    import torch
+    from oracle import physicsnet_oracle as po
+    from paig_reproduction_b200.physics_models import PhysicsNet
+    spec = po.TASKS["spring_color"]
+    dev = torch.device("cuda", 0)
+    net = PhysicsNet("spring_color", 100, 1, "spring_ode_cell", spec.seq_len, spec.input_steps, spec.pred_steps, 3.0, False, True,
+                     spec.H * spec.H, "conv_encoder", "conv_st_decoder", device=dev)
+    net.load_state_dict(po.init_state_dict(spec, 0), strict=True)
+    xs = [po.synthetic_frames(spec, 23, spec.seq_len, seed).to(dev) for seed in (5, 6)]
+    ref = []
+    for x in xs:
+        losses = net.train_step(x).clone()
+        ref.append((net.flat_gradients().clone(), losses))
+    for rep in range(2):
+        for x, (g_ref, l_ref) in zip(xs, ref):
+            losses = net.train_step_graph(x)
+            assert torch.equal(net.flat_gradients(), g_ref) and torch.equal(losses, l_ref)
+    assert len(net._step_graphs) == 2 and all(v is not False for v in net._step_graphs.values())
+    assert net.graph_replay_launches >= 4 * 40
+    with torch.no_grad():                               # what optimizer.step() does: in place
+        for p in net.parameters():
+            if p.dtype == torch.float32:
+                p.mul_(1.0 + 1e-3)
+    eager = (net.train_step(xs[0]).clone(), net.flat_gradients().clone())
+    assert not torch.equal(eager[1], ref[0][0])
+    losses = net.train_step_graph(xs[0])
+    assert len(net._step_graphs) == 2                   # same addresses: the recorded graph is reused
+    assert torch.equal(net.flat_gradients(), eager[1]) and torch.equal(losses, eager[0])
