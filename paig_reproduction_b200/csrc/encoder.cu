@@ -728,6 +728,10 @@ static size_t enc_tail_smem(bool bwd) {
 }
 constexpr int kTailStride = kHidden * kHidden + 2 * kHidden + kHidden + 4;      // floats per CTA partial
 
+// workspace whose A^T (the encoder.l1 weight gradient's operand) the last encoder_forward of this thread transposed on a side
+// stream; a backward pass on any other workspace, or after a forward that ran without side streams, transposes it itself
+static thread_local const float* g_At_ws = nullptr;
+
 static bool l1_wgrad_on_tc(int M) {
     static const bool tc_off = getenv("PAIG_NO_TCGEN05") != nullptr;
     static const int tc_mask = getenv("PAIG_TC_MASK") ? atoi(getenv("PAIG_TC_MASK")) : 6;
@@ -773,7 +777,9 @@ int encoder_forward(const paig_task* t, const paig_params* p, const Layout& L, c
                         st) != cudaSuccess)
         return check_launch("copy enc_masks");
     const int M = d.n * L.N;
-    if (sd && l1_wgrad_on_tc(M)) {
+    g_At_ws = nullptr;
+    if (sd && l1_wgrad_on_tc(M) && !(t->flags & PAIG_FLAG_INFERENCE)) {       // (an inference workspace has no room for it)
+        g_At_ws = ws;                                                           // the backward pass on THIS workspace may skip it
         // the backward's encoder.l1 weight gradient wants A^T: transpose it now, beside the MLP / rollout / decoder chain
         sd->fork1();
         float* At = ws + L.tc_scratch + (size_t)L.K * kHidden + (size_t)kHidden * M;
@@ -858,7 +864,7 @@ int encoder_backward(const paig_task* t, const paig_params* p, const paig_params
         cudaStream_t wst = sd ? sd->s1 : st;
         float* Wt = ws + L.tc_scratch;                       // [K][200]
         float* dHt = Wt + (size_t)L.K * kHidden;             // [200][M]
-        float* At = dHt + (size_t)kHidden * M;               // [K][M]   (already filled by encoder_forward when sd)
+        float* At = dHt + (size_t)kHidden * M;               // [K][M]   (already filled by encoder_forward when g_At_ws == ws)
         float* wpart = sd ? ws + L.partials2 : ws + L.partials;
         const size_t wpart_floats = sd ? L.partials2_floats : L.partials_floats;
         int sp = -1;
@@ -868,7 +874,7 @@ int encoder_backward(const paig_task* t, const paig_params* p, const paig_params
         if (l1_wgrad_on_tc(M)) {
             // dW1[200,K] = dH1^T[200,M] . A^T[K,M]^T : both operands transposed once so that M is the contiguous K axis
             if ((rc = transpose(ws + L.dH1, dHt, M, kHidden, wst))) return rc;
-            if (!sd && (rc = transpose(ws + L.A, At, M, L.K, wst))) return rc;
+            if (!(sd && g_At_ws == ws) && (rc = transpose(ws + L.A, At, M, L.K, wst))) return rc;
             sp = gemm_tc_partials(dHt, At, kHidden, L.K, M, false, wpart, wpart_floats, "tc_l1_wgrad", wst);
             if (sp == 0) return 2;
         }

@@ -102,17 +102,32 @@ static int finalize_losses(const paig_task* t, const Layout& L, float* ws, float
     return 0;
 }
 
+namespace {
+struct SideScope {                                   // side streams live for exactly one step call (fused, forward or backward)
+    Side* sd;
+    explicit SideScope(cudaStream_t st) : sd(side_begin(st)) {}
+    ~SideScope() { if (sd) side_end(); }
+};
+}  // namespace
+
 int step_forward(const paig_task* t, const paig_params* p, const float* x, int B, const paig_outputs* out, float* ws,
                  cudaStream_t st) {
     const Layout L = make_layout(t, B);
+    // the split forward / backward calls of the drop-in module take the same side streams as the fused step (the
+    // VariableFromNetwork branch beside the encoder, the l1 transposes, the twelve weight-gradient launches ...): serial,
+    // that path ran 0.15 ms behind (tools/dropin_probe.py)
+    SideScope scope(st);
+    Side* sd = scope.sd;
     int rc = forward_common(t, p, L, x, out, ws, st);
-    if (rc) return rc;
+    if (rc) { if (sd) { sd->join1(); sd->join2(); } return rc; }
     DecSeg A, R;
     segments(t, L, ws, x, &A, &R);
     A.frames = out ? out->recons_out : nullptr;
     R.frames = out ? out->output_seq : nullptr;
-    if ((rc = decode_run(t, ws + L.consts, A, R, false, nullptr, nullptr, 0, st))) return rc;
-    return finalize_losses(t, L, ws, out ? out->losses : nullptr, st);
+    rc = decode_run(t, ws + L.consts, A, R, false, nullptr, nullptr, 0, st);
+    if (!rc) rc = finalize_losses(t, L, ws, out ? out->losses : nullptr, st);
+    if (sd) { sd->join1(); sd->join2(); }             // every fork is joined before the call returns
+    return rc;
 }
 
 // Everything after the decoder's backward: d_seq / d_enc_pos / d_consts are complete in the workspace.
@@ -152,11 +167,26 @@ static bool refuse_inference(const paig_task* t, const char* what) {
     return true;
 }
 
+static int step_backward_body(const paig_task* t, const paig_params* p, const paig_params* g, const float* x, int B,
+                              const float* d_output_seq, const float* d_recons_out, const float* d_enc_pos,
+                              const float* d_pos_vel_seq, float* ws, cudaStream_t st, const Layout& L, Side* sd);
+
 int step_backward(const paig_task* t, const paig_params* p, const paig_params* g, const float* x, int B,
                   const float* d_output_seq, const float* d_recons_out, const float* d_enc_pos,
                   const float* d_pos_vel_seq, float* ws, cudaStream_t st) {
     if (refuse_inference(t, "step_backward")) return 1;
     const Layout L = make_layout(t, B);
+    const Dims& d = L.d;
+    SideScope scope(st);
+    Side* sd = scope.sd;
+    const int rc_all = step_backward_body(t, p, g, x, B, d_output_seq, d_recons_out, d_enc_pos, d_pos_vel_seq, ws, st, L, sd);
+    if (sd) { sd->join1(); sd->join2(); }
+    return rc_all;
+}
+
+static int step_backward_body(const paig_task* t, const paig_params* p, const paig_params* g, const float* x, int B,
+                              const float* d_output_seq, const float* d_recons_out, const float* d_enc_pos,
+                              const float* d_pos_vel_seq, float* ws, cudaStream_t st, const Layout& L, Side* sd) {
     const Dims& d = L.d;
     const size_t seq_fl = (size_t)B * (d.steps + 1) * 4 * d.n, ep_fl = (size_t)L.N * 2 * d.n;
     if (cudaMemsetAsync(ws + L.d_seq, 0, seq_fl * sizeof(float), st) != cudaSuccess) return check_launch("memset");
@@ -187,16 +217,13 @@ int step_backward(const paig_task* t, const paig_params* p, const paig_params* g
         launch(axpy_kernel, dim3(cdiv(seq_fl, 256)), dim3(256), 0, st, ws + L.d_seq, d_pos_vel_seq, (long)seq_fl);
         if ((rc = check_launch("axpy"))) return rc;
     }
-    return backward_tail(t, p, g, L, x, ws, st);
+    // the VariableFromNetwork backward only needs the decoder's d_consts: beside the rollout / encoder chain
+    if (sd) {
+        sd->fork1();
+        if ((rc = templates_backward(t, p, g, ws + L.consts, ws + L.hidden, ws + L.d_consts, ws + L.tmpl_scratch, sd->s1))) return rc;
+    }
+    return backward_tail(t, p, g, L, x, ws, st, sd != nullptr);
 }
-
-namespace {
-struct SideScope {                                   // side streams live for exactly one fused step
-    Side* sd;
-    explicit SideScope(cudaStream_t st) : sd(side_begin(st)) {}
-    ~SideScope() { if (sd) side_end(); }
-};
-}  // namespace
 
 int step_fused(const paig_task* t, const paig_params* p, const paig_params* g, const float* x, int B,
                const paig_outputs* out, float* ws, cudaStream_t st) {

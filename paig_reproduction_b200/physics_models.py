@@ -228,8 +228,11 @@ class PhysicsNet(BaseNetTorch):
 
     def live_parameter_names(self, with_rollout: bool = True) -> List[str]:
         """state_dict keys that receive a gradient in a LIVE step, in state_dict order."""
-        names = []
-        for k, _ in self.named_parameters():
+        cache = self.__dict__.setdefault("_live_names", {})
+        if with_rollout in cache:
+            return list(cache[with_rollout])
+        names = cache[with_rollout] = []
+        for k, _ in self._named():
             if k.startswith("encoder.") and not (k.startswith("encoder." + self._unet + ".") or k.startswith("encoder.l")):
                 continue                                              # the unused UNet
             if k.startswith("rollout_cell."):
@@ -238,19 +241,47 @@ class PhysicsNet(BaseNetTorch):
             if k.startswith("velocity_encoder.") and not with_rollout:
                 continue
             names.append(k)
-        return names
+        return list(names)
+
+    # The table is ~95 pointers; filled field by field through ctypes attribute access (and with named_parameters() walked
+    # three times per step) the Python side of the drop-in path cost more than the GPU side (2.4 ms of host time per 2.2 ms
+    # of kernels, tools/dropin_probe.py).  paig_params is a flat array of 8-byte pointers, so every state_dict key is
+    # resolved ONCE to its slot index (by filling a probe struct with sentinels through _abi.fill_params, the one place that
+    # knows the layout) and a table is then ~95 integer stores.
+    def _slot_of(self) -> Dict[str, int]:
+        bind = self.__dict__.get("_slot_index")
+        if bind is None:
+            names = [k for k, _ in self._named()]
+            probe = _abi.Params()
+            sent = {k: 0x1000 + 8 * i for i, k in enumerate(names)}
+            _abi.fill_params(probe, lambda k: sent[k], names, self._unet, self._n_convs, self.alt_vel, self.cell_kind)
+            arr = (ctypes.c_uint64 * (ctypes.sizeof(_abi.Params) // 8)).from_buffer(probe)
+            where = {int(v): i for i, v in enumerate(arr) if v}
+            bind = self.__dict__["_slot_index"] = {k: where[sent[k]] for k in names if sent[k] in where}
+        return bind
+
+    def _named(self):
+        """(name, parameter) pairs in state_dict order, walked once: the modules of a PhysicsNet never change."""
+        named = self.__dict__.get("_named_params")
+        if named is None:
+            named = self.__dict__["_named_params"] = list(self.named_parameters())
+        return named
 
     def _param_table(self, tensors: Dict[str, torch.Tensor]) -> _abi.Params:
         p = _abi.Params()
-        for t in tensors.values():
+        arr = (ctypes.c_uint64 * (ctypes.sizeof(_abi.Params) // 8)).from_buffer(p)
+        slot = self._slot_of()
+        for k, t in tensors.items():
+            i = slot.get(k)
+            if i is None:
+                continue
             if not (t.is_cuda and t.is_contiguous()):
                 raise _lib.PaigError("parameters must be contiguous CUDA tensors (no CPU path exists)")
-        _abi.fill_params(p, lambda k: tensors[k].data_ptr(), tensors.keys(), self._unet, self._n_convs, self.alt_vel,
-                         self.cell_kind)
+            arr[i] = t.data_ptr()
         return p
 
     def _params_now(self) -> Dict[str, torch.Tensor]:
-        return {k: v.data for k, v in self.named_parameters()}
+        return {k: v.data for k, v in self._named()}
 
     def _workspace(self, T: int, B: int, fresh: bool, inference: bool = False) -> torch.Tensor:
         lib = _lib.load()
@@ -303,6 +334,20 @@ class PhysicsNet(BaseNetTorch):
         self._last_ws = weakref.ref(ws)           # parity tests read the ReLU decisions of this forward back (tests/stage_checks.py)
         return out
 
+    def _alloc_grads(self, params, live):
+        """Fresh gradient tensors for the live parameters: one allocation per dtype, carved into views (90 separate
+        torch.empty_like calls were 0.3 ms of host time per step)."""
+        by_dtype: Dict[torch.dtype, list] = {}
+        for k in live:
+            by_dtype.setdefault(params[k].dtype, []).append(k)
+        grads = {}
+        for dt, names in by_dtype.items():
+            sizes = [(params[k].numel() + 3) & ~3 for k in names]          # every view starts 16-byte aligned (fp32) or better
+            flat = torch.empty(sum(sizes), dtype=dt, device=self.device)
+            for k, chunk in zip(names, flat.split_with_sizes(sizes)):
+                grads[k] = chunk[:params[k].numel()].view(params[k].shape)
+        return grads
+
     def _run_backward(self, inp, ws, d_out, d_rec, d_enc_pos, d_seq):
         lib = _lib.load()
         x = inp.detach().contiguous().float()
@@ -313,7 +358,7 @@ class PhysicsNet(BaseNetTorch):
         if self.input_steps == 1:
             # physics_models.py:222-223: vel = zeros, the velocity encoder is not on the graph -> grad stays None
             live = [k for k in live if not k.startswith("velocity_encoder.")]
-        grads = {k: torch.empty_like(params[k]) for k in live}
+        grads = self._alloc_grads(params, live)
         P, G = self._param_table(params), self._param_table(grads)
         tk = self._task(T)
 
@@ -325,7 +370,7 @@ class PhysicsNet(BaseNetTorch):
                                           *[None if t is None else t.data_ptr() for t in keep], ws.data_ptr(), stream),
                    "paig_step_backward")
         result = []
-        for k, p in self.named_parameters():
+        for k, p in self._named():
             g = grads.get(k)
             if g is not None and not with_rollout and (k.startswith("velocity_encoder.") or k.startswith("rollout_cell.")):
                 g = None                 # STALE mode: nothing flows through the rollout, grads stay None
@@ -339,7 +384,7 @@ class PhysicsNet(BaseNetTorch):
     def conv_feedforward(self, inp):                                  # physics_models.py:204-245
         self._check_input(inp)
         self.input = inp
-        params = [p for _, p in self.named_parameters()]
+        params = [p for _, p in self._named()]
         output_seq, recons_out, enc_pos, pos_vel_seq, enc_masks, masked = _Step.apply(self, inp, torch.is_grad_enabled(), *params)
         last = self._last
         self.recons_out = recons_out
@@ -509,7 +554,7 @@ class PhysicsNet(BaseNetTorch):
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(lib.paig_step_fused(ctypes.byref(tk), ctypes.byref(P), ctypes.byref(G), x.data_ptr(), B,
                                        ctypes.byref(O), ws.data_ptr(), stream), "paig_step_fused")
-        for k, p in self.named_parameters():
+        for k, p in self._named():
             v = self._grad_views.get(k)
             if v is not None:
                 p.grad = v
@@ -542,7 +587,7 @@ class PhysicsNet(BaseNetTorch):
         graph, launches = entry
         graph.replay()
         self.graph_replay_launches = getattr(self, "graph_replay_launches", 0) + launches
-        for k, p in self.named_parameters():
+        for k, p in self._named():
             v = self._grad_views.get(k)
             if v is not None:
                 p.grad = v
