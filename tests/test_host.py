@@ -115,3 +115,39 @@ def test_flat_gradient_order_puts_the_unet_last(task):
     early = sum(params[k].numel() for k in order[:first_conv])
     total = sum(params[k].numel() for k in order)
     assert early / total > (0.9 if task != "mnist_spring_color" else 0.85)
+
+
+@pytest.mark.parametrize("task,alt_vel", [(t, False) for t in RUNNER_ARGS] + [("spring_color", True)])
+def test_parameter_table_slot_index_equals_the_field_by_field_fill(task, alt_vel):
+    """PhysicsNet fills paig_params through a slot index resolved once per net (physics_models._slot_of) instead of ctypes
+    attribute access per call; byte for byte it must be the table _abi.fill_params builds, for every task / cell / velocity
+    encoder variant, and the live-gradient allocation must hand out disjoint, correctly shaped, 16-byte aligned views."""
+    from paig_reproduction_b200.physics_models import PhysicsNet
+    args = list(RUNNER_ARGS[task])
+    args[8] = alt_vel
+    net = PhysicsNet(*args, device="cpu")
+    names = [k for k, _ in net.named_parameters()]
+    fake = {k: 0x7f0000000000 + 4096 * i for i, k in enumerate(names)}
+    want = _abi.Params()
+    _abi.fill_params(want, lambda k: fake[k], names, net._unet, net._n_convs, net.alt_vel, net.cell_kind)
+    got = _abi.Params()
+    arr = (ctypes.c_uint64 * (ctypes.sizeof(_abi.Params) // 8)).from_buffer(got)
+    slot = net._slot_of()
+    for k in names:
+        if k in slot:
+            arr[slot[k]] = fake[k]
+    assert bytes(want) == bytes(got)
+    assert len(set(slot.values())) == len(slot)
+    # live parameters all have a slot; parameters without one are exactly those the step never touches
+    assert all(k in slot for k in net.live_parameter_names())
+    params = {k: v.data for k, v in net.named_parameters()}
+    live = net.live_parameter_names()
+    grads = net._alloc_grads(params, live)
+    spans = []
+    for k in live:
+        g = grads[k]
+        assert g.shape == params[k].shape and g.dtype == params[k].dtype and g.is_contiguous()
+        assert g.data_ptr() % 16 == 0
+        spans.append((g.data_ptr(), g.data_ptr() + g.numel() * g.element_size()))
+    spans.sort()
+    assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:]))
