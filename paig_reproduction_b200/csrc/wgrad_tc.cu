@@ -9,18 +9,17 @@
 //
 //      D[(ky, co), (kx, ci)] = sum_K  G_ky[co][K] . X_kx[ci][K],   G_ky = g shifted by 1-ky rows, X_kx = in shifted by kx-1 columns
 //
-// with M = 3 Cout rows (tiles of 128) and N = 3 Cin columns (tiles of <= 192): every MMA is 128 x (96..208) x 8 instead of
-// nine products 128 x Cin x 8, which is what keeps the tensor pipe fed (an M = 128 tf32 MMA costs ~100 cycles of
-// operand-A fetch whatever its N).
+// with M = 3 Cout rows (tiles of 128) and N = 3 x 32 input-channel columns (+ 16: the bias column) per CTA: MMAs of
+// 128 x 224 x 8 and 128 x 112 x 8 instead of nine products 128 x Cin x 8, which is what keeps the tensor pipe fed (an
+// M = 128 tf32 MMA costs ~100 cycles of operand-A fetch whatever its N).
 //   * K block = 32 pixels = one 128-byte swizzle span: one image row at 32 px, half a row at 64 px, 2 / 4 rows at 16 / 8 px.
-//   * Raw boxes arrive through two 4-D tensor maps into a ring of kRaw stages (deep enough to cover the TMA latency:
-//     with the operands landing straight in the two MMA stages the kernel was latency bound, 52 TFLOP/s).  The row shift
-//     of G_ky is the box's y coordinate; the TMA unit's out-of-bounds zero fill is the padding.
+//   * Raw boxes arrive through two 4-D tensor maps (no swizzle) into a small ring of landing stages.  The row shift of G_ky
+//     is the box's y coordinate; the TMA unit's out-of-bounds zero fill is the padding.
 //   * The innermost TMA coordinate must stay 16-byte aligned (tools/tma_probe.cu), so the column shift cannot be a
 //     coordinate: the input arrives once per K block as a raw box with a 4-pixel halo on both sides.  Converter warps
-//     split every raw element into hi | lo and write the MMA tiles in the 128-byte-swizzled K-major layout themselves:
-//     16-byte chunks for the gradient rows, scalar stores with lanes along K for the three shifted input copies (both
-//     conflict free).
+//     split every raw element into hi | lo and write the MMA tiles in the 128-byte-swizzled K-major layout themselves,
+//     16 bytes at a time: a chunk of a gradient row goes to the chunk index XOR (row & 7); a thread splits the six raw
+//     neighbours of four input pixels once and stores the three column-shifted chunks from registers (conflict free).
 //   * 3xTF32 (hi.hi + hi.lo + lo.hi, split as in gemm_tc.cu) in two MMAs per K step: [main | corr] += G_hi x [X_hi | X_lo]
 //     (N doubled, one fetch of G_hi -- the kernel is bound by the MMAs' shared-memory operand fetch) and corr += G_lo x X_hi.
 //     The tensor core accumulates with truncation, so the accumulators run in chains of `chain` K blocks that the
@@ -29,6 +28,9 @@
 //     unshifted gradient rows (ky = 1) are sum g.
 //   * grid = (K splits, M tiles, N tiles); every CTA writes its share of partial `split` in the final
 //     [co][ci][3][3] | [co] layout, folded in fixed order by the shared reduce_partials pass (bit-reproducible).
+//   * All loop bookkeeping of the single-thread roles is incremental: with `kb / bpf`, `%` by run-time values in the TMA
+//     producer's loop that one thread's trip time (~1900 cycles) bounded the kernel.
+// Measured bounds and the experiments behind the constants below: profiles/r2w_wgrad_tc_probe.txt.
 #include "common.cuh"
 #include "internal.h"
 
@@ -43,12 +45,11 @@
 namespace paig {
 namespace {
 
-constexpr int kWcConvWarps = 12;       // converter warps (the conversion is latency bound: 8 -> 12 warps 0.69 -> ? us per K block)
+constexpr int kWcConvWarps = 12;       // converter warps (8 and 12 measure the same: the kernel is bound by shared-memory bandwidth)
 constexpr int kWcThreads = 64 + 32 * kWcConvWarps;   // warp 0 TMA producer, warp 1 MMA issuer / TMEM owner, then the converters
 constexpr int kWcConv = 32 * kWcConvWarps;
 constexpr int kWcDrain = 256;          // the first eight converter warps also drain the main accumulator
-constexpr int kWcStages = 3;            // converted (hi | lo) operand stages the MMAs read (with two, conversion and MMAs of a
-                                        // stage alternate and the kernel runs at the SUM of both)
+constexpr int kWcStages = 3;           // converted (hi | lo) operand stages the MMAs read (2 with a deeper raw ring measures the same)
 constexpr int kWcMaxRaw = 6;           // raw TMA landing stages
 constexpr int kWcMaxCt = 32;           // input channels per N tile
 constexpr unsigned kWcABytes = 128 * 128;
