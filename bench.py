@@ -211,8 +211,8 @@ def main():
     use_graph = os.environ.get("PAIG_BENCH_GRAPH", "1") != "0" and not dp.overlap
     if use_graph:
         try:
-            for i in range(POOL):
-                graph_step(i)
+            for i in range(POOL):                 # no collective in here: a rank that fails to record cannot strand the others
+                net.train_step_graph(dev_pool[i])
             torch.cuda.synchronize(dev)
             use_graph = all(v is not False for v in net._step_graphs.values())
         except Exception:                         # noqa: BLE001 -- eager launches are always available
