@@ -79,7 +79,10 @@ class FusedOptimizer:
 
 class DeviceIterator:
     """iterators.py:4-40 (DataIterator) over a uint8 array [N, T, H, W, C] kept on the device.  Index shuffling uses
-    numpy's global RNG exactly like the reference, so a seeded run visits the same sequences in the same order."""
+    numpy's global RNG exactly like the reference, so a seeded run visits the same sequences in the same order.  The epoch
+    bookkeeping (reset_iteration / get_epoch / reset_epoch / the wrap-around in next_batch) is a near-verbatim restatement of
+    the reference class, assert message included: identical RNG draws and epoch boundaries require identical control flow;
+    what differs is where the data lives and how a batch is gathered (paig_gather_batch_u8)."""
 
     def __init__(self, X_u8: np.ndarray, device, conv: bool = True):
         assert X_u8.dtype == np.uint8 and X_u8.ndim == 5
